@@ -1,0 +1,28 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "slow: larger CPU case (still part of the default CPU suite)")
+
+
+@pytest.fixture(scope="session")
+def oracle_built():
+    """Build the CPU checkers once per session (liborc.so always; _ref only if /root/reference exists)."""
+    from oracle import pyoracle
+
+    pyoracle.build()
+    return pyoracle
+
+
+def pytest_collection_modifyitems(config, items):
+    # GPU tests must fail loudly, not skip silently, when selected with -m gpu on a box without the
+    # extension; but on the CPU box `-m "not gpu"` deselects them, so nothing to do here.
+    pass

@@ -1,0 +1,188 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference (oracle/_ref/libref.so).
+
+Run in the build container, where /root/reference exists:
+    make -C oracle all && python tests/golden/make_golden.py
+The GPU box has no /root/reference; the committed fixtures (and the prebuilt _ref, which travels
+with the snapshot but is never committed) are what the tests there compare against.
+
+Every array called ref_* below was produced by the reference's own C++ (through oracle/ref_shim.cpp);
+nothing here comes from the restatement or from the CUDA path.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from oracle import pyoracle as po  # noqa: E402
+from tests import workloads as wl  # noqa: E402
+
+REF_EXAMPLES = "/root/reference/examples"
+
+
+def save(name, **kw):
+    p = os.path.join(HERE, name)
+    np.savez_compressed(p, **kw)
+    print("%-22s %8.1f KB" % (name, os.path.getsize(p) / 1024))
+
+
+def toy():
+    U, img = wl.toy_unary(), wl.toy_image()
+    out = {"U": U, "img": img}
+    for nt in range(4):
+        c = po.CRF((10, 10), 2, "ref")
+        c.setUnaryEnergy(U)
+        c.addPairwiseBilateral(2, 2, img, 3, normalization=nt)
+        out["ref_Q_nt%d" % nt] = np.ascontiguousarray(c.inference(10))
+    # values the survey recorded from the reference's Python build
+    assert np.allclose(out["ref_Q_nt3"][0, :5], [0.9659939, 0.9665577, 0.9684372, 0.9732122, 0.9716119], atol=2e-7)
+    assert np.allclose(out["ref_Q_nt1"][0, :3], [0.96293056, 0.9643855, 0.9684238], atol=2e-7)
+    assert np.allclose(out["ref_Q_nt2"][0, :3], [0.9689846, 0.9687308, 0.96852446], atol=2e-7)
+    # generic path with utils.create_pairwise_bilateral feature order (row, col, r, g, b)
+    yy, xx = np.meshgrid(np.arange(10), np.arange(10), indexing="ij")
+    f = np.concatenate([np.stack([yy, xx]).astype(np.float32) / 2, np.rollaxis(img, 2).astype(np.float32) / 2])
+    f = np.ascontiguousarray(f.reshape(5, -1))
+    c = po.CRF(100, 2, "ref")
+    c.setUnaryEnergy(U)
+    c.addPairwiseEnergy(f, 3)
+    out["generic_feats"] = f
+    out["ref_Q_generic"] = np.ascontiguousarray(c.inference(10))
+    save("toy.npz", **out)
+
+
+def lattices():
+    rng = np.random.default_rng(7)
+    out = {}
+    cases = [(2, 96), (5, 101), (3, 7), (4, 64), (5, 1), (1, 33), (7, 50)]
+    out["cases"] = np.array(cases, np.int32)
+    for ci, (d, N) in enumerate(cases):
+        f = (rng.standard_normal((d, N)) * 2.5).astype(np.float32)
+        lt = po.Lattice(f, "ref")
+        off, bary, rank, nbr = lt.dump()
+        out["f%d" % ci] = f
+        out["ref_off%d" % ci] = off
+        out["ref_bary%d" % ci] = bary
+        out["ref_nbr%d" % ci] = nbr
+        for L in (1, 2, 3, 21):
+            x = rng.random((N, L), dtype=np.float32)
+            out["x%d_L%d" % (ci, L)] = x
+            out["ref_y%d_L%d" % (ci, L)] = lt.filter(x)
+    save("lattice_small.npz", **out)
+
+
+def softmax():
+    rng = np.random.default_rng(11)
+    out = {}
+    for L in (1, 2, 3, 4, 5, 8, 21, 150):
+        x = (rng.standard_normal((64, L)) * 15).astype(np.float32)
+        x[0] = -300.0
+        x[1, 0] = 200.0
+        out["x_L%d" % L] = x
+        out["ref_y_L%d" % L] = po.exp_and_normalize(x, "ref")
+    save("softmax.npz", **out)
+
+
+def model_small():
+    W, H, L = 40, 30, 21
+    rng = np.random.default_rng(3)
+    img = wl.smooth_image(H, W, seed=3, grid=8)
+    U = wl.softmax_unary(H, W, L, seed=3, grid=8)
+    Mx = wl.matrix_compat(L, seed=3)
+    Dg = (-rng.random(L) * 4).astype(np.float32)
+    out = {"img": img, "U": U, "Mx": Mx, "Dg": Dg}
+    compats = {"potts": (3.0, 10.0), "diag": (Dg, 4.0), "matrix": (Mx, Mx)}
+    for cname, (cg, cb) in compats.items():
+        for nt in range(4):
+            c = po.CRF((W, H), L, "ref")
+            c.setUnaryEnergy(U)
+            c.addPairwiseGaussian(3, cg, normalization=nt)
+            c.addPairwiseBilateral(20, 13, img, cb, normalization=nt)
+            out["ref_Q_%s_nt%d" % (cname, nt)] = np.ascontiguousarray(c.inference(5))
+            Q = np.array(c.startInference())
+            kls = []
+            for _ in range(3):
+                kls.append(c.klDivergence(Q))
+                c.stepInference(Q)
+            out["ref_KL_%s_nt%d" % (cname, nt)] = np.array(kls)
+    # no unary at all (densecrf.cpp:117 / :178-186)
+    c = po.CRF((W, H), L, "ref")
+    c.addPairwiseGaussian(3, 3.0)
+    out["ref_Q_nounary"] = np.ascontiguousarray(c.inference(2))
+    out["ref_Q0_nounary"] = np.ascontiguousarray(c.startInference())
+    save("model_small.npz", **out)
+
+
+def cfg1():
+    import cv2
+
+    img = cv2.imread(os.path.join(REF_EXAMPLES, "im1.png"))
+    anno = cv2.imread(os.path.join(REF_EXAMPLES, "anno1.png")).astype(np.uint32)
+    lbl = anno[:, :, 0] + (anno[:, :, 1] << 8) + (anno[:, :, 2] << 16)
+    colors, labels = np.unique(lbl, return_inverse=True)
+    assert 0 in colors
+    n_labels = len(set(labels.flat)) - 1
+    labels = labels.reshape(-1)
+    # pydensecrf.utils.unary_from_labels(labels, n_labels, gt_prob=0.7, zero_unsure=True)  (utils.py:6-46)
+    n_e, p_e = -np.log(0.3 / (n_labels - 1)), -np.log(0.7)
+    U = np.full((n_labels, labels.size), n_e, dtype="float32")
+    U[labels - 1, np.arange(labels.size)] = p_e
+    U[:, labels == 0] = -np.log(1.0 / n_labels)
+    H, W = img.shape[:2]
+    out = {"img": img, "labels": labels.astype(np.uint8), "n_labels": n_labels, "U": U}
+    # use_2d branch (examples/inference.py:72-90)
+    c = po.CRF((W, H), n_labels, "ref")
+    c.setUnaryEnergy(U)
+    c.addPairwiseGaussian(3, 3.0)
+    c.addPairwiseBilateral(80, 13, img, 10.0)
+    out["ref_Q_2d"] = np.ascontiguousarray(c.inference(5))
+    Q = np.array(c.startInference())
+    kls = []
+    for _ in range(5):
+        kls.append(c.klDivergence(Q))
+        c.stepInference(Q)
+    out["ref_KL_2d"] = np.array(kls)
+    # identical to what the reference's own Python extension (built from /root/reference with the
+    # recipe in SURVEY.md section 8c) prints for this input in this container
+    assert kls == [-543710.7136065669, -890203.4196090547, -919601.7338062561, -921429.4572714955,
+                   -922284.9388205523], kls
+    if os.path.exists("/tmp/refpy_Q.npy"):  # Q from that Python build, when it is lying around
+        assert np.array_equal(np.load("/tmp/refpy_Q.npy"), out["ref_Q_2d"])
+    # generic branch (examples/inference.py:91-111): features in (row, col[, b, g, r]) order
+    yy, xx = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
+    mesh = np.stack([yy, xx]).astype(np.float32)
+    fg = np.ascontiguousarray((mesh / 3).reshape(2, -1))
+    fb = np.ascontiguousarray(np.concatenate([mesh / 80, np.rollaxis(img, 2).astype(np.float32) / 13]).reshape(5, -1))
+    c = po.CRF(W * H, n_labels, "ref")
+    c.setUnaryEnergy(U)
+    c.addPairwiseEnergy(fg, 3.0)
+    c.addPairwiseEnergy(fb, 10.0)
+    out["ref_Q_generic"] = np.ascontiguousarray(c.inference(5))
+    save("cfg1_im1.npz", **out)
+
+
+def mid():
+    """160x120, 21 labels, the cfg 2 recipe at 1/12 scale, 10 iterations."""
+    W, H, L = 160, 120, 21
+    img = wl.smooth_image(H, W, seed=5, grid=16)
+    U = wl.softmax_unary(H, W, L, seed=5, grid=8)
+    c = po.CRF((W, H), L, "ref")
+    c.setUnaryEnergy(U)
+    c.addPairwiseGaussian(3, 3.0)
+    c.addPairwiseBilateral(80, 13, img, 10.0)
+    Q = np.ascontiguousarray(c.inference(10))
+    srt = np.sort(Q, axis=0)
+    save("mid_160x120.npz", seed=5, ref_MAP=np.argmax(Q, axis=0).astype(np.uint8),
+         ref_margin=(srt[-1] - srt[-2]).astype(np.float32), ref_Q_sub=Q[:, ::5].copy())
+
+
+if __name__ == "__main__":
+    po.build()
+    assert po.available("ref"), "oracle/_ref/libref.so missing: /root/reference not visible?"
+    toy()
+    lattices()
+    softmax()
+    model_small()
+    cfg1()
+    mid()
