@@ -1,0 +1,166 @@
+/*
+ * dcrf_b200.h -- C-ABI of libdcrf_b200.so, the B200 (sm_100a) mean-field engine behind
+ * pydensecrf's Python surface.
+ *
+ * The reference has no C interface: its Cython layer binds the C++ classes directly
+ * (pydensecrf/densecrf.pxd:4-84).  This header is the boundary the build introduces instead; each
+ * entry point replaces exactly one call the reference's .pyx makes into C++ and names it below as
+ * "replaces <file>:<line>".  Paths are relative to /root/reference/.  INTEGRATION.md shows the
+ * .pyx/.pxd a maintainer of the reference would write against this header.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch/numpy types.
+ *   - every function returns a dcrf_status; on failure dcrf_last_error() (thread-local) describes it.
+ *     DCRF_EINVAL -> ValueError, DCRF_ECUDA -> RuntimeError, DCRF_ENOMEM -> MemoryError.
+ *   - host arrays are read during the call only (copied / uploaded before return), like the
+ *     reference, which copies every numpy input at its boundary (pydensecrf/eigen_impl.cpp:19-25).
+ *   - "LxN row-major" = numpy (L, N) C-order;  "NxL pixel-major" = the memory of an
+ *     Eigen::MatrixXf(L, N), which is what pydensecrf's MatrixXf exposes through the buffer
+ *     protocol (pydensecrf/eigen.pyx:58-98: shape (L,N), strides (4, 4L)).
+ *   - a handle is not thread-safe (same contract as the reference); distinct handles are
+ *     independent and may live on different GPUs.  All work of a handle runs on its own stream.
+ *   - there is no CPU fallback: any entry that computes needs a CUDA device and fails with
+ *     DCRF_ECUDA otherwise.
+ */
+#ifndef DCRF_B200_H
+#define DCRF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCRF_ABI_VERSION 1
+
+typedef enum { DCRF_OK = 0, DCRF_EINVAL = 1, DCRF_ECUDA = 2, DCRF_ENOMEM = 3 } dcrf_status;
+
+/* pydensecrf/densecrf/include/pairwise.h:32-42 (same numeric values) */
+typedef enum { DCRF_NO_NORMALIZATION = 0, DCRF_NORMALIZE_BEFORE = 1, DCRF_NORMALIZE_AFTER = 2, DCRF_NORMALIZE_SYMMETRIC = 3 } dcrf_norm_type;
+typedef enum { DCRF_CONST_KERNEL = 0, DCRF_DIAG_KERNEL = 1, DCRF_FULL_KERNEL = 2 } dcrf_kernel_type;
+/* which LabelCompatibility the .pyx's _labelcomp() would have built (pydensecrf/densecrf.pyx:11-20) */
+typedef enum {
+  DCRF_COMPAT_POTTS = 0,   /* compat_data[1]:   out = -w * Q          labelcompatibility.cpp:46-48 */
+  DCRF_COMPAT_DIAGONAL = 1,/* compat_data[L]:   out = diag(w) * Q     labelcompatibility.cpp:66-69 */
+  DCRF_COMPAT_MATRIX = 2   /* compat_data[L*L] row-major: out = 0.5(m+m^T) * Q   :79-84 */
+} dcrf_compat_kind;
+
+typedef struct dcrf_model dcrf_t;   /* a DenseCRF / DenseCRF2D object */
+typedef struct dcrf_mat dcrf_mat_t; /* an eigen.MatrixXf / VectorXf object: host mirror + device buffer */
+
+const char* dcrf_last_error(void);
+int dcrf_abi_version(void);
+/* number of visible CUDA devices; 0 when there is no driver/GPU (never fails) */
+int dcrf_device_count(void);
+
+/* ---- model lifetime --------------------------------------------------------------------------- */
+/* replaces `new c_DenseCRF(nvar, nlabels)`            pydensecrf/densecrf.pyx:58  (densecrf.cpp:39)
+ * device < 0 selects $DCRF_B200_DEVICE, else device 0. */
+dcrf_status dcrf_create(int nvar, int nlabels, int device, dcrf_t** out);
+/* replaces `new c_DenseCRF2D(w, h, nlabels)`          pydensecrf/densecrf.pyx:110 (densecrf.cpp:47) */
+dcrf_status dcrf_create_2d(int width, int height, int nlabels, int device, dcrf_t** out);
+/* replaces `del self._this`                           pydensecrf/densecrf.pyx:68 */
+void dcrf_destroy(dcrf_t* m);
+
+/* ---- unary ------------------------------------------------------------------------------------ */
+/* replaces setUnaryEnergy(c_matrixXf(u))              pydensecrf/densecrf.pyx:87  (densecrf.cpp:89; unary.cpp:42-46)
+ * and `new ConstUnaryEnergy` + setUnaryEnergy(u.move()) pydensecrf/densecrf.pyx:41,78.   u: LxN row-major. */
+dcrf_status dcrf_set_unary_const(dcrf_t* m, const float* u_LxN);
+/* replaces setUnaryEnergy(c_matrixXf(L), c_matrixXf(f)) pydensecrf/densecrf.pyx:89 and LogisticUnary :46,78
+ * (unary.cpp:48-52: U = Lmat * f).   Lmat: L x F row-major, f: F x N row-major. */
+dcrf_status dcrf_set_unary_logistic(dcrf_t* m, const float* Lmat_LxF, int F, const float* f_FxN);
+
+/* ---- pairwise terms (each builds one permutohedral lattice on the GPU) ------------------------- */
+/* replaces addPairwiseEnergy(c_matrixXf(features), _labelcomp(compat), kernel, normalization)
+ *                                                      pydensecrf/densecrf.pyx:75 (densecrf.cpp:54; pairwise.cpp:116-122,40-62;
+ *                                                      permutohedral.cpp:140-321).   feat: d x N row-major. */
+dcrf_status dcrf_add_pairwise_energy(dcrf_t* m, const float* feat_dxN, int d, int compat_kind,
+                                     const float* compat_data, int kernel_type, int norm_type);
+/* replaces _this2d.addPairwiseGaussian(sx, sy, ...)   pydensecrf/densecrf.pyx:124 (densecrf.cpp:61-69) */
+dcrf_status dcrf_add_pairwise_gaussian(dcrf_t* m, float sx, float sy, int compat_kind, const float* compat_data,
+                                       int kernel_type, int norm_type);
+/* replaces _this2d.addPairwiseBilateral(sx,sy,sr,sg,sb,&rgbim[0,0,0], ...)  pydensecrf/densecrf.pyx:138 (densecrf.cpp:70-81)
+ * rgb: H x W x 3 bytes, channel order as given. */
+dcrf_status dcrf_add_pairwise_bilateral(dcrf_t* m, float sx, float sy, float sr, float sg, float sb,
+                                        const uint8_t* rgb_HxWx3, int compat_kind, const float* compat_data,
+                                        int kernel_type, int norm_type);
+
+/* ---- inference -------------------------------------------------------------------------------- */
+/* replaces eigen.MatrixXf().wrap(_this.inference(niter))   pydensecrf/densecrf.pyx:92 (densecrf.cpp:115-131)
+ * *Q is a new matrix (L x N) whose data stays on the device until its host view is requested. */
+dcrf_status dcrf_inference(dcrf_t* m, int n_iterations, dcrf_mat_t** Q);
+/* replaces _this.startInference()                     pydensecrf/densecrf.pyx:95 (densecrf.cpp:178-186) */
+dcrf_status dcrf_start_inference(dcrf_t* m, dcrf_mat_t** Q);
+/* replaces _this.stepInference(Q.m, tmp1.m, tmp2.m)   pydensecrf/densecrf.pyx:98 (densecrf.cpp:187-201)
+ * Q is updated in place.  tmp1/tmp2 are accepted for signature compatibility and may be NULL; the
+ * engine keeps its own scratch, so they are left untouched. */
+dcrf_status dcrf_step_inference(dcrf_t* m, dcrf_mat_t* Q, dcrf_mat_t* tmp1, dcrf_mat_t* tmp2);
+/* replaces _this.klDivergence(Q.m)                    pydensecrf/densecrf.pyx:101 (densecrf.cpp:214-235) */
+dcrf_status dcrf_kl_divergence(dcrf_t* m, dcrf_mat_t* Q, double* out);
+/* DenseCRF::currentMap (densecrf.cpp:202-211; unwrapped in the reference's .pyx:61-62):
+ * per-pixel argmax of Q computed on the device, first maximum wins; labels_N receives N int16. */
+dcrf_status dcrf_current_map(dcrf_t* m, dcrf_mat_t* Q, int16_t* labels_N);
+
+/* ---- matrices: the eigen.MatrixXf / eigen.VectorXf objects of the reference -------------------- */
+/* replaces eigen.MatrixXf() (empty 0x0)               pydensecrf/eigen.pyx:62-66 */
+dcrf_status dcrf_mat_create_empty(dcrf_mat_t** out);
+/* replaces c_buf2matf(&arr[0,0], h, w)                pydensecrf/eigen.pyx:52 (eigen_impl.cpp:19-25): row-major in,
+ * stored pixel-major (col-major).  Works without a GPU. */
+dcrf_status dcrf_mat_from_host(const float* rowmajor, int rows, int cols, dcrf_mat_t** out);
+/* replaces c_buf2vecf(&arr[0], n)                     pydensecrf/eigen.pyx:7 (eigen_impl.cpp:9-12): n x 1 */
+dcrf_status dcrf_vec_from_host(const float* data, int n, dcrf_mat_t** out);
+void dcrf_mat_destroy(dcrf_mat_t* a);
+int dcrf_mat_rows(const dcrf_mat_t* a);
+int dcrf_mat_cols(const dcrf_mat_t* a);
+/* replaces self.m.data() in __getbuffer__             pydensecrf/eigen.pyx:85: pointer to rows*cols floats, col-major
+ * (strides (4, 4*rows)), valid until the matrix is destroyed.  Downloads from the device first if the
+ * device copy is newer.  The caller may write through it: call dcrf_mat_release_host() when the view
+ * ends so the next device use re-uploads. */
+dcrf_status dcrf_mat_host_ptr(dcrf_mat_t* a, float** ptr);
+/* a buffer view ended (the .pyx's __releasebuffer__, pydensecrf/eigen.pyx:97): the host copy may have been written */
+void dcrf_mat_release_host(dcrf_mat_t* a);
+
+/* ---- measurement (bench.py) ------------------------------------------------------------------- */
+dcrf_status dcrf_synchronize(dcrf_t* m);
+/* CUDA events on the model's own stream: start, then stop returns elapsed milliseconds */
+dcrf_status dcrf_timer_start(dcrf_t* m);
+dcrf_status dcrf_timer_stop(dcrf_t* m, float* ms);
+/* per-kernel-class timing: when enabled every launch is bracketed by events on the model's stream.
+ * dcrf_profile_read fills up to `cap` entries; returns the count via *n. */
+typedef struct {
+  char name[32];
+  int launches;
+  float ms_total;
+} dcrf_prof_entry;
+dcrf_status dcrf_profile_enable(dcrf_t* m, int on);
+dcrf_status dcrf_profile_read(dcrf_t* m, dcrf_prof_entry* out, int cap, int* n, int reset);
+/* kernels launched by this model since creation (bench.py's gpu_launches) */
+int64_t dcrf_launch_count(const dcrf_t* m);
+/* write a >L2-sized scratch buffer on the model's stream (timing hygiene between iterations) */
+dcrf_status dcrf_flush_l2(dcrf_t* m);
+/* upload a host unary into a device-resident matrix / run inference entirely on device buffers:
+ * same as dcrf_inference but reuses *Q if it already has the right shape (no allocation in the timed loop) */
+dcrf_status dcrf_inference_into(dcrf_t* m, int n_iterations, dcrf_mat_t* Q);
+
+/* ---- introspection for the parity tests -------------------------------------------------------- */
+int dcrf_num_pairwise(const dcrf_t* m);
+/* lattice of pairwise term k: feature dims d, pixels N, vertices V (incl. phantom vertices) */
+dcrf_status dcrf_lattice_info(const dcrf_t* m, int k, int* d, int* N, int* V);
+/* any pointer may be NULL.  offset/bary: N*(d+1) (vertex id / barycentric weight per pixel corner, ids in the
+ * reference's first-touch order); keys: V*d int16; nbr: (d+1)*V*2 (-1 = absent); norm: N. */
+dcrf_status dcrf_lattice_dump(dcrf_t* m, int k, int32_t* offset, float* bary, int16_t* keys, int32_t* nbr,
+                              float* norm);
+/* Permutohedral::compute of term k (permutohedral.cpp:596-604) on a host array, NxL pixel-major in/out;
+ * no normalisation, no compatibility. */
+dcrf_status dcrf_lattice_filter(dcrf_t* m, int k, const float* in_NxL, int L, float* out_NxL);
+/* PairwisePotential::apply of term k (pairwise.cpp:173-178) on a device matrix -> new matrix */
+dcrf_status dcrf_pairwise_apply(dcrf_t* m, int k, dcrf_mat_t* Q, dcrf_mat_t** out);
+/* 0 = pick automatically, 1 = force the staged (unfused) iteration, 2 = force the fused iteration (fails if
+ * the model has a term the fused kernel cannot take) */
+dcrf_status dcrf_set_iteration_mode(dcrf_t* m, int mode);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCRF_B200_H */

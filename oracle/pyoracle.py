@@ -231,6 +231,11 @@ class CRF:
         self.lib.crf_step(self.h, _ptr(q))
         Q[...] = q.T
 
+    def step_raw(self, q_NxL):
+        """stepInference in place on a C-contiguous (N, L) float32 array (no layout copies)."""
+        assert q_NxL.flags.c_contiguous and q_NxL.dtype == np.float32 and q_NxL.shape == (self.N, self.L)
+        self.lib.crf_step(self.h, _ptr(q_NxL))
+
     def klDivergence(self, Q):
         q = np.ascontiguousarray(Q.T, dtype=np.float32)
         return float(self.lib.crf_kl(self.h, _ptr(q)))

@@ -1,0 +1,562 @@
+# cython: language_level=3, boundscheck=False, wraparound=False
+# distutils: language = c++
+"""Python surface of pydensecrf, bound to the C-ABI of libdcrf_b200.so (include/dcrf_b200.h).
+
+Mirrors the classes, signatures, argument meaning and error behaviour of the reference's Cython
+layer (pydensecrf/densecrf.pyx and pydensecrf/eigen.pyx in /root/reference), but every method is a
+thin call into the C-ABI; no Eigen, no C++ classes, no CPU compute path.  `pydensecrf_b200.densecrf`
+and `pydensecrf_b200.eigen` re-export the names under the reference's module layout.
+"""
+from numbers import Number
+import enum
+
+from cpython.buffer cimport PyBUF_WRITABLE
+from libc.stdint cimport int16_t, int32_t, int64_t, uint8_t
+
+
+cdef extern from "dcrf_b200.h" nogil:
+    ctypedef struct dcrf_t:
+        pass
+    ctypedef struct dcrf_mat_t:
+        pass
+    ctypedef struct dcrf_prof_entry:
+        char name[32]
+        int launches
+        float ms_total
+    const char* dcrf_last_error()
+    int dcrf_abi_version()
+    int dcrf_device_count()
+    int dcrf_create(int nvar, int nlabels, int device, dcrf_t** out)
+    int dcrf_create_2d(int width, int height, int nlabels, int device, dcrf_t** out)
+    void dcrf_destroy(dcrf_t* m)
+    int dcrf_set_unary_const(dcrf_t* m, const float* u)
+    int dcrf_set_unary_logistic(dcrf_t* m, const float* Lmat, int F, const float* f)
+    int dcrf_add_pairwise_energy(dcrf_t* m, const float* feat, int d, int ckind, const float* cdata, int ktype, int ntype)
+    int dcrf_add_pairwise_gaussian(dcrf_t* m, float sx, float sy, int ckind, const float* cdata, int ktype, int ntype)
+    int dcrf_add_pairwise_bilateral(dcrf_t* m, float sx, float sy, float sr, float sg, float sb, const uint8_t* rgb,
+                                    int ckind, const float* cdata, int ktype, int ntype)
+    int dcrf_inference(dcrf_t* m, int n, dcrf_mat_t** Q)
+    int dcrf_inference_into(dcrf_t* m, int n, dcrf_mat_t* Q)
+    int dcrf_start_inference(dcrf_t* m, dcrf_mat_t** Q)
+    int dcrf_step_inference(dcrf_t* m, dcrf_mat_t* Q, dcrf_mat_t* t1, dcrf_mat_t* t2)
+    int dcrf_kl_divergence(dcrf_t* m, dcrf_mat_t* Q, double* out)
+    int dcrf_current_map(dcrf_t* m, dcrf_mat_t* Q, int16_t* labels)
+    int dcrf_mat_create_empty(dcrf_mat_t** out)
+    int dcrf_mat_from_host(const float* rowmajor, int rows, int cols, dcrf_mat_t** out)
+    int dcrf_vec_from_host(const float* data, int n, dcrf_mat_t** out)
+    void dcrf_mat_destroy(dcrf_mat_t* a)
+    int dcrf_mat_rows(const dcrf_mat_t* a)
+    int dcrf_mat_cols(const dcrf_mat_t* a)
+    int dcrf_mat_host_ptr(dcrf_mat_t* a, float** ptr)
+    void dcrf_mat_release_host(dcrf_mat_t* a)
+    int dcrf_synchronize(dcrf_t* m)
+    int dcrf_timer_start(dcrf_t* m)
+    int dcrf_timer_stop(dcrf_t* m, float* ms)
+    int dcrf_profile_enable(dcrf_t* m, int on)
+    int dcrf_profile_read(dcrf_t* m, dcrf_prof_entry* out, int cap, int* n, int reset)
+    int64_t dcrf_launch_count(const dcrf_t* m)
+    int dcrf_flush_l2(dcrf_t* m)
+    int dcrf_num_pairwise(const dcrf_t* m)
+    int dcrf_lattice_info(const dcrf_t* m, int k, int* d, int* N, int* V)
+    int dcrf_lattice_dump(dcrf_t* m, int k, int32_t* offset, float* bary, int16_t* keys, int32_t* nbr, float* norm)
+    int dcrf_lattice_filter(dcrf_t* m, int k, const float* inp, int L, float* out)
+    int dcrf_pairwise_apply(dcrf_t* m, int k, dcrf_mat_t* Q, dcrf_mat_t** out)
+    int dcrf_set_iteration_mode(dcrf_t* m, int mode)
+
+
+class KernelType(enum.IntEnum):
+    # pydensecrf/densecrf/include/pairwise.h:38-42
+    CONST_KERNEL = 0
+    DIAG_KERNEL = 1
+    FULL_KERNEL = 2
+
+
+class NormalizationType(enum.IntEnum):
+    # pydensecrf/densecrf/include/pairwise.h:32-37
+    NO_NORMALIZATION = 0
+    NORMALIZE_BEFORE = 1
+    NORMALIZE_AFTER = 2
+    NORMALIZE_SYMMETRIC = 3
+
+
+# the README and examples/inference.py use the module-level spellings (dcrf.DIAG_KERNEL, ...)
+CONST_KERNEL = KernelType.CONST_KERNEL
+DIAG_KERNEL = KernelType.DIAG_KERNEL
+FULL_KERNEL = KernelType.FULL_KERNEL
+NO_NORMALIZATION = NormalizationType.NO_NORMALIZATION
+NORMALIZE_BEFORE = NormalizationType.NORMALIZE_BEFORE
+NORMALIZE_AFTER = NormalizationType.NORMALIZE_AFTER
+NORMALIZE_SYMMETRIC = NormalizationType.NORMALIZE_SYMMETRIC
+
+
+cdef int _check(int status) except -1:
+    if status == 0:
+        return 0
+    msg = dcrf_last_error().decode("utf-8", "replace")
+    if status == 1:
+        raise ValueError(msg)
+    if status == 3:
+        raise MemoryError(msg)
+    raise RuntimeError(msg)
+
+
+def abi_version():
+    return dcrf_abi_version()
+
+
+def device_count():
+    """Number of CUDA devices the engine can see (0 without a GPU/driver)."""
+    return dcrf_device_count()
+
+
+# ------------------------------------------------------------------------------------------------
+# eigen.pyx surface
+# ------------------------------------------------------------------------------------------------
+cdef class VectorXf:
+    """Same buffer contract as the reference's VectorXf (pydensecrf/eigen.pyx:11-45)."""
+    cdef dcrf_mat_t* h
+    cdef Py_ssize_t shape[1]
+    cdef Py_ssize_t strides[1]
+
+    def __cinit__(self):
+        self.h = NULL
+        self.shape[0] = 0
+        self.strides[0] = 0
+
+    def __dealloc__(self):
+        if self.h != NULL:
+            dcrf_mat_destroy(self.h)
+            self.h = NULL
+
+    cdef VectorXf _adopt(self, dcrf_mat_t* h):
+        if self.h != NULL:
+            dcrf_mat_destroy(self.h)
+        self.h = h
+        self.shape[0] = dcrf_mat_rows(h)
+        self.strides[0] = sizeof(float)
+        return self
+
+    def __getbuffer__(self, Py_buffer* buf, int flags):
+        cdef float* p = NULL
+        if self.h == NULL:
+            _check(dcrf_mat_create_empty(&self.h))
+        _check(dcrf_mat_host_ptr(self.h, &p))
+        buf.buf = <char*>p
+        buf.format = 'f'
+        buf.internal = NULL
+        buf.itemsize = sizeof(float)
+        buf.len = self.shape[0] * buf.itemsize
+        buf.ndim = 1
+        buf.obj = self
+        buf.readonly = 0
+        buf.shape = self.shape
+        buf.strides = self.strides
+        buf.suboffsets = NULL
+
+    def __releasebuffer__(self, Py_buffer* buf):
+        if self.h != NULL:
+            dcrf_mat_release_host(self.h)
+
+
+def vectorXf(float[::1] arr not None):
+    cdef dcrf_mat_t* h = NULL
+    cdef const float* p = &arr[0] if arr.shape[0] > 0 else NULL
+    _check(dcrf_vec_from_host(p, <int>arr.shape[0], &h))
+    return VectorXf()._adopt(h)
+
+
+cdef class MatrixXf:
+    """Handle-backed stand-in for the reference's Eigen-owning MatrixXf (pydensecrf/eigen.pyx:58-98).
+
+    Exposes the buffer protocol with shape (rows, cols) and strides (4, 4*rows) (column-major, i.e.
+    the labels of one variable are contiguous), writable.  The data may live on the GPU; the first
+    buffer request downloads it."""
+    cdef dcrf_mat_t* h
+    cdef Py_ssize_t shape[2]
+    cdef Py_ssize_t strides[2]
+    cdef object owner
+
+    def __cinit__(self):
+        self.h = NULL
+        self.owner = None
+        self.shape[0] = self.shape[1] = 0
+        self.strides[0] = self.strides[1] = 0
+
+    def __dealloc__(self):
+        if self.h != NULL:
+            dcrf_mat_destroy(self.h)
+            self.h = NULL
+
+    cdef dcrf_mat_t* handle(self) except NULL:
+        if self.h == NULL:
+            _check(dcrf_mat_create_empty(&self.h))
+        return self.h
+
+    cdef MatrixXf _adopt(self, dcrf_mat_t* h, object owner):
+        if self.h != NULL:
+            dcrf_mat_destroy(self.h)
+        self.h = h
+        self.owner = owner
+        self._refresh()
+        return self
+
+    cdef void _refresh(self):
+        self.shape[0] = dcrf_mat_rows(self.h)
+        self.shape[1] = dcrf_mat_cols(self.h)
+        # Eigen's MatrixXf is column-major (pydensecrf/eigen.pyx:76-79)
+        self.strides[0] = sizeof(float)
+        self.strides[1] = self.shape[0] * self.strides[0]
+
+    def __getbuffer__(self, Py_buffer* buf, int flags):
+        cdef float* p = NULL
+        cdef dcrf_mat_t* h = self.handle()
+        cdef int st
+        with nogil:
+            st = dcrf_mat_host_ptr(h, &p)
+        _check(st)
+        self._refresh()
+        buf.buf = <char*>p
+        buf.format = 'f'
+        buf.internal = NULL
+        buf.itemsize = sizeof(float)
+        buf.len = self.shape[0] * self.shape[1] * buf.itemsize
+        buf.ndim = 2
+        buf.obj = self
+        buf.readonly = 0
+        buf.shape = self.shape
+        buf.strides = self.strides
+        buf.suboffsets = NULL
+
+    def __releasebuffer__(self, Py_buffer* buf):
+        if self.h != NULL:
+            dcrf_mat_release_host(self.h)
+
+
+def matrixXf(float[:, ::1] arr not None):
+    cdef dcrf_mat_t* h = NULL
+    cdef const float* p = &arr[0, 0] if arr.shape[0] > 0 and arr.shape[1] > 0 else NULL
+    _check(dcrf_mat_from_host(p, <int>arr.shape[0], <int>arr.shape[1], &h))
+    return MatrixXf()._adopt(h, None)
+
+
+# ------------------------------------------------------------------------------------------------
+# densecrf.pyx surface
+# ------------------------------------------------------------------------------------------------
+cdef class _Compat:
+    """What _labelcomp() decides in the reference (pydensecrf/densecrf.pyx:11-20): a number is Potts,
+    a 1-D float32 buffer Diagonal, a 2-D float32 buffer Matrix, anything deeper a ValueError."""
+    cdef int kind
+    cdef float scalar
+    cdef float[::1] vec
+    cdef float[:, ::1] mat
+
+    def __cinit__(self, compat, int nlabels):
+        if isinstance(compat, Number):
+            self.kind = 0
+            self.scalar = compat
+        elif memoryview(compat).ndim == 1:
+            self.kind = 1
+            self.vec = compat  # raises "Buffer dtype mismatch" (ValueError) for non-float32, like the reference
+            if self.vec.shape[0] != nlabels:
+                raise ValueError("Bad shape for diagonal label compatibility (Need ({},), got ({},))".format(nlabels, self.vec.shape[0]))
+        elif memoryview(compat).ndim == 2:
+            self.kind = 2
+            self.mat = compat
+            if self.mat.shape[0] != nlabels or self.mat.shape[1] != nlabels:
+                raise ValueError("Bad shape for matrix label compatibility (Need {}, got {})".format((nlabels, nlabels), (self.mat.shape[0], self.mat.shape[1])))
+        else:
+            raise ValueError("LabelCompatibility of dimension >2 not meaningful.")
+
+    cdef const float* data(self):
+        if self.kind == 0:
+            return &self.scalar
+        if self.kind == 1:
+            return &self.vec[0]
+        return &self.mat[0, 0]
+
+
+cdef class Unary:
+    """Base of ConstUnary / LogisticUnary (pydensecrf/densecrf.pyx:23-46).  setUnary() consumes it,
+    mirroring the ownership hand-off of the reference's Unary.move()."""
+    cdef object _u   # float32 C-contiguous arrays kept until consumed
+    cdef object _f
+    cdef bint _logistic
+
+
+cdef class ConstUnary(Unary):
+    def __cinit__(self, float[:, ::1] u not None):
+        self._u = u.copy()
+        self._f = None
+        self._logistic = False
+
+
+cdef class LogisticUnary(Unary):
+    def __cinit__(self, float[:, ::1] L not None, float[:, ::1] f not None):
+        if L.shape[1] != f.shape[0]:
+            raise ValueError("Bad shapes for logistic unary: L is {}, f is {}".format((L.shape[0], L.shape[1]), (f.shape[0], f.shape[1])))
+        self._u = L.copy()
+        self._f = f.copy()
+        self._logistic = True
+
+
+cdef int _device_arg(dict kw) except? -2:
+    dev = kw.get("device", None)
+    return -1 if dev is None else int(dev)
+
+
+cdef class DenseCRF:
+    cdef dcrf_t* _h
+    cdef int _nlabel
+    cdef int _nvar
+
+    def __cinit__(self, int nvar, int nlabels, *_, **kw):
+        # like the reference, the base __cinit__ also runs for DenseCRF2D (with w, h as its first two
+        # arguments) and must then leave construction to the subclass (pydensecrf/densecrf.pyx:51-63)
+        self._h = NULL
+        if not isinstance(self, DenseCRF2D):
+            _check(dcrf_create(nvar, nlabels, _device_arg(kw), &self._h))
+        self._nvar = nvar
+        self._nlabel = nlabels
+
+    def __dealloc__(self):
+        if self._h != NULL:
+            dcrf_destroy(self._h)
+            self._h = NULL
+
+    def addPairwiseEnergy(self, float[:, ::1] features not None, compat, kernel=DIAG_KERNEL, normalization=NORMALIZE_SYMMETRIC):
+        if features.shape[1] != self._nvar:
+            raise ValueError("Bad shape for pairwise energy (Need (?, {}), got {})".format(self._nvar, (features.shape[0], features.shape[1])))
+        cdef _Compat c = _Compat(compat, self._nlabel)
+        cdef int kt = int(KernelType(kernel)), nt = int(NormalizationType(normalization))
+        cdef int d = <int>features.shape[0], st
+        if d < 1:
+            raise ValueError("Bad shape for pairwise energy (need at least one feature row)")
+        cdef const float* fp = &features[0, 0]
+        cdef const float* cp = c.data()
+        with nogil:
+            st = dcrf_add_pairwise_energy(self._h, fp, d, c.kind, cp, kt, nt)
+        _check(st)
+
+    def setUnary(self, Unary u not None):
+        cdef float[:, ::1] a, b
+        cdef int st
+        if u._u is None:
+            raise ValueError("This Unary object was already handed to a DenseCRF (setUnary takes ownership).")
+        a = u._u
+        if u._logistic:
+            b = u._f
+            if a.shape[0] != self._nlabel or b.shape[1] != self._nvar:
+                raise ValueError("Bad shape for logistic unary (Need L ({}, F) and f (F, {}), got {} and {})".format(
+                    self._nlabel, self._nvar, (a.shape[0], a.shape[1]), (b.shape[0], b.shape[1])))
+            with nogil:
+                st = dcrf_set_unary_logistic(self._h, &a[0, 0], <int>a.shape[1], &b[0, 0])
+        else:
+            if a.shape[0] != self._nlabel or a.shape[1] != self._nvar:
+                raise ValueError("Bad shape for unary energy (Need {}, got {})".format((self._nlabel, self._nvar), (a.shape[0], a.shape[1])))
+            with nogil:
+                st = dcrf_set_unary_const(self._h, &a[0, 0])
+        _check(st)
+        u._u = None
+        u._f = None
+
+    def setUnaryEnergy(self, float[:, ::1] u not None, float[:, ::1] f=None):
+        if u.shape[0] != self._nlabel or u.shape[1] != self._nvar:
+            raise ValueError("Bad shape for unary energy (Need {}, got {})".format((self._nlabel, self._nvar), (u.shape[0], u.shape[1])))
+        cdef int st
+        if f is None:
+            with nogil:
+                st = dcrf_set_unary_const(self._h, &u[0, 0])
+        else:
+            # the reference forwards (u, f) to LogisticUnaryEnergy(L=u, feature=f) after the shape check
+            # above (pydensecrf/densecrf.pyx:80-89), so f has to be (nvar, nvar) for L*f to be a unary
+            if f.shape[0] != u.shape[1] or f.shape[1] != self._nvar:
+                raise ValueError("Bad shape for logistic feature (Need {}, got {})".format((u.shape[1], self._nvar), (f.shape[0], f.shape[1])))
+            with nogil:
+                st = dcrf_set_unary_logistic(self._h, &u[0, 0], <int>u.shape[1], &f[0, 0])
+        _check(st)
+
+    def inference(self, int niter):
+        cdef dcrf_mat_t* q = NULL
+        cdef int st
+        with nogil:
+            st = dcrf_inference(self._h, niter, &q)
+        _check(st)
+        return MatrixXf()._adopt(q, self)
+
+    def startInference(self):
+        cdef dcrf_mat_t* q = NULL
+        cdef int st
+        with nogil:
+            st = dcrf_start_inference(self._h, &q)
+        _check(st)
+        return MatrixXf()._adopt(q, self), MatrixXf(), MatrixXf()
+
+    def stepInference(self, MatrixXf Q not None, MatrixXf tmp1 not None, MatrixXf tmp2 not None):
+        cdef dcrf_mat_t* q = Q.handle()
+        cdef dcrf_mat_t* t1 = tmp1.handle()
+        cdef dcrf_mat_t* t2 = tmp2.handle()
+        cdef int st
+        with nogil:
+            st = dcrf_step_inference(self._h, q, t1, t2)
+        _check(st)
+
+    def klDivergence(self, MatrixXf Q not None):
+        cdef dcrf_mat_t* q = Q.handle()
+        cdef double out = 0.0
+        cdef int st
+        with nogil:
+            st = dcrf_kl_divergence(self._h, q, &out)
+        _check(st)
+        return out
+
+    # ---- additions (not in the reference's wrapper) ------------------------------------------------
+    def inferenceInto(self, int niter, MatrixXf Q not None):
+        """inference(niter) written into an existing MatrixXf (no allocation when shapes match)."""
+        cdef dcrf_mat_t* q = Q.handle()
+        cdef int st
+        with nogil:
+            st = dcrf_inference_into(self._h, niter, q)
+        _check(st)
+        Q.owner = self
+        Q._refresh()
+        return Q
+
+    def currentMap(self, MatrixXf Q not None):
+        """Per-variable argmax of Q computed on the device (DenseCRF::currentMap, densecrf.cpp:202-211):
+        int16 array of length nvar; only 2 bytes per variable cross PCIe instead of the 4*nlabels of Q."""
+        import numpy as np
+        out = np.empty(self._nvar, dtype=np.int16)
+        cdef int16_t[::1] o = out
+        cdef dcrf_mat_t* q = Q.handle()
+        cdef int st
+        with nogil:
+            st = dcrf_current_map(self._h, q, &o[0])
+        _check(st)
+        return out
+
+    def synchronize(self):
+        _check(dcrf_synchronize(self._h))
+
+    def _timer_start(self):
+        _check(dcrf_timer_start(self._h))
+
+    def _timer_stop(self):
+        cdef float ms = 0
+        cdef int st
+        with nogil:
+            st = dcrf_timer_stop(self._h, &ms)
+        _check(st)
+        return ms
+
+    def _profile_enable(self, bint on):
+        _check(dcrf_profile_enable(self._h, 1 if on else 0))
+
+    def _profile_read(self, bint reset=True):
+        cdef dcrf_prof_entry ent[64]
+        cdef int n = 0
+        _check(dcrf_profile_read(self._h, ent, 64, &n, 1 if reset else 0))
+        out = {}
+        for i in range(min(n, 64)):
+            out[ent[i].name.decode()] = (ent[i].launches, ent[i].ms_total)
+        return out
+
+    def _launch_count(self):
+        return dcrf_launch_count(self._h)
+
+    def _flush_l2(self):
+        _check(dcrf_flush_l2(self._h))
+
+    def _set_iteration_mode(self, int mode):
+        _check(dcrf_set_iteration_mode(self._h, mode))
+
+    def _num_pairwise(self):
+        return dcrf_num_pairwise(self._h)
+
+    def _lattice_info(self, int k):
+        cdef int d = 0, N = 0, V = 0
+        _check(dcrf_lattice_info(self._h, k, &d, &N, &V))
+        return d, N, V
+
+    def _lattice_dump(self, int k):
+        """(offset (N,d+1) int32, bary (N,d+1) f32, keys (V,d) int16, nbr (d+1,V,2) int32, norm (N,) f32)"""
+        import numpy as np
+        d, N, V = self._lattice_info(k)
+        off = np.zeros((N, d + 1), np.int32)
+        bary = np.zeros((N, d + 1), np.float32)
+        keys = np.zeros((max(V, 1), d), np.int16)
+        nbr = np.zeros((d + 1, max(V, 1), 2), np.int32)
+        norm = np.zeros(N, np.float32)
+        cdef int32_t[:, ::1] o = off
+        cdef float[:, ::1] b = bary
+        cdef int16_t[:, ::1] ky = keys
+        cdef int32_t[:, :, ::1] nb = nbr
+        cdef float[::1] nm = norm
+        cdef int st
+        with nogil:
+            st = dcrf_lattice_dump(self._h, k, &o[0, 0], &b[0, 0], &ky[0, 0], &nb[0, 0, 0], &nm[0])
+        _check(st)
+        return off, bary, keys[:V], nbr[:, :V], norm
+
+    def _lattice_filter(self, int k, float[:, ::1] x_NxL not None):
+        """Permutohedral::compute of term k on a (N, L) pixel-major array."""
+        import numpy as np
+        out = np.empty((x_NxL.shape[0], x_NxL.shape[1]), np.float32)
+        cdef float[:, ::1] o = out
+        cdef int L = <int>x_NxL.shape[1], st
+        d, N, V = self._lattice_info(k)
+        if x_NxL.shape[0] != N:
+            raise ValueError("need (N, L) input with N = {}".format(N))
+        with nogil:
+            st = dcrf_lattice_filter(self._h, k, &x_NxL[0, 0], L, &o[0, 0])
+        _check(st)
+        return out
+
+    def _pairwise_apply(self, int k, MatrixXf Q not None):
+        cdef dcrf_mat_t* o = NULL
+        cdef dcrf_mat_t* q = Q.handle()
+        cdef int st
+        with nogil:
+            st = dcrf_pairwise_apply(self._h, k, q, &o)
+        _check(st)
+        return MatrixXf()._adopt(o, self)
+
+
+cdef class DenseCRF2D(DenseCRF):
+    cdef int _w
+    cdef int _h2
+
+    def __cinit__(self, int w, int h, int nlabels, *_, **kw):
+        _check(dcrf_create_2d(w, h, nlabels, _device_arg(kw), &self._h))
+        self._w = w
+        self._h2 = h
+        self._nvar = w * h
+        self._nlabel = nlabels
+
+    def addPairwiseGaussian(self, sxy, compat, kernel=DIAG_KERNEL, normalization=NORMALIZE_SYMMETRIC):
+        if isinstance(sxy, Number):
+            sxy = (sxy, sxy)
+        cdef _Compat c = _Compat(compat, self._nlabel)
+        cdef int kt = int(KernelType(kernel)), nt = int(NormalizationType(normalization)), st
+        cdef float sx = sxy[0], sy = sxy[1]
+        cdef const float* cp = c.data()
+        with nogil:
+            st = dcrf_add_pairwise_gaussian(self._h, sx, sy, c.kind, cp, kt, nt)
+        _check(st)
+
+    def addPairwiseBilateral(self, sxy, srgb, unsigned char[:, :, ::1] rgbim not None, compat, kernel=DIAG_KERNEL, normalization=NORMALIZE_SYMMETRIC):
+        if isinstance(sxy, Number):
+            sxy = (sxy, sxy)
+        if isinstance(srgb, Number):
+            srgb = (srgb, srgb, srgb)
+        if rgbim.shape[0] != self._h2 or rgbim.shape[1] != self._w:
+            raise ValueError("Bad shape for pairwise bilateral (Need {}, got {})".format((self._h2, self._w, 3), (rgbim.shape[0], rgbim.shape[1], rgbim.shape[2])))
+        if rgbim.shape[2] != 3:
+            raise ValueError("addPairwiseBilateral only works for RGB images. For other types, use `utils.create_pairwise_bilateral` to construct your own pairwise energy and add it through `addPairwiseEnergy`.")
+        cdef _Compat c = _Compat(compat, self._nlabel)
+        cdef int kt = int(KernelType(kernel)), nt = int(NormalizationType(normalization)), st
+        cdef float sx = sxy[0], sy = sxy[1], sr = srgb[0], sg = srgb[1], sb = srgb[2]
+        cdef const float* cp = c.data()
+        cdef const uint8_t* ip = &rgbim[0, 0, 0]
+        with nogil:
+            st = dcrf_add_pairwise_bilateral(self._h, sx, sy, sr, sg, sb, ip, c.kind, cp, kt, nt)
+        _check(st)

@@ -1,0 +1,953 @@
+// Host driver and C-ABI of libdcrf_b200.so (include/dcrf_b200.h).
+//
+// Replaces the model layer of the reference (paths relative to /root/reference/pydensecrf/densecrf/):
+//   DenseCRF / DenseCRF2D            src/densecrf.cpp:39-131,178-235
+//   DenseKernel::initLattice/filter  src/pairwise.cpp:40-80
+//   PairwisePotential::apply         src/pairwise.cpp:173-178
+//   Const/LogisticUnaryEnergy        src/unary.cpp:42-52
+// and the Eigen-backed matrix objects of pydensecrf/eigen.pyx.  Everything lattice- or label-sized
+// lives in HBM for the life of the model; one CUDA stream per model; no CPU compute path.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+
+#include "common.h"
+
+namespace dcrf {
+
+static thread_local std::string g_last_error;
+
+void fail_cuda(cudaError_t e, const char* expr, const char* file, int line) {
+  cudaGetLastError();  // clear sticky-less errors
+  const char* base = std::strrchr(file, '/');
+  throw Error(e == cudaErrorMemoryAllocation ? DCRF_ENOMEM : DCRF_ECUDA,
+              std::string("CUDA error: ") + cudaGetErrorString(e) + " [" + expr + "] at " + (base ? base + 1 : file) +
+                  ":" + std::to_string(line));
+}
+
+// ---- profiler ----------------------------------------------------------------------------------
+cudaEvent_t Profiler::get_event() {
+  if (!free_events.empty()) {
+    cudaEvent_t e = free_events.back();
+    free_events.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  DCRF_CUDA(cudaEventCreate(&e));
+  return e;
+}
+int Profiler::index_of(const char* name) {
+  for (size_t i = 0; i < recs.size(); i++)
+    if (recs[i].name == name) return (int)i;
+  recs.emplace_back();
+  recs.back().name = name;
+  return (int)recs.size() - 1;
+}
+void Profiler::collect() {
+  for (auto& r : recs) {
+    for (auto& pr : r.pending) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) r.ms += ms;
+      free_events.push_back(pr.first);
+      free_events.push_back(pr.second);
+    }
+    r.pending.clear();
+  }
+}
+void Profiler::destroy() {
+  collect();
+  for (cudaEvent_t e : free_events) cudaEventDestroy(e);
+  free_events.clear();
+}
+
+// ---- pinned host memory pool: result matrices are re-used across inference calls ----------------
+struct PinnedPool {
+  std::mutex mu;
+  std::multimap<size_t, void*> free_blocks;
+  size_t cached = 0;
+  static constexpr size_t kMaxCached = 8ull << 30;
+  void* get(size_t bytes) {
+    {
+      std::lock_guard<std::mutex> g(mu);
+      auto it = free_blocks.find(bytes);
+      if (it != free_blocks.end()) {
+        void* p = it->second;
+        free_blocks.erase(it);
+        cached -= bytes;
+        return p;
+      }
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      throw Error(DCRF_ENOMEM, "cudaHostAlloc failed for " + std::to_string(bytes) + " bytes");
+    }
+    return p;
+  }
+  void put(void* p, size_t bytes) {
+    std::lock_guard<std::mutex> g(mu);
+    if (cached + bytes > kMaxCached) {
+      cudaFreeHost(p);
+      return;
+    }
+    free_blocks.emplace(bytes, p);
+    cached += bytes;
+  }
+};
+static PinnedPool g_pinned;
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) DCRF_CUDA(cudaSetDevice(dev));
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+}  // namespace dcrf
+
+using namespace dcrf;
+
+// ---- matrix object -----------------------------------------------------------------------------
+struct dcrf_mat {
+  int rows = 0, cols = 0;
+  float* host = nullptr;  // rows*cols floats, col-major (pixel-major); malloc'd or pinned
+  bool host_pinned = false;
+  float* dev = nullptr;   // cols rows of RowLayout(rows).Lp floats
+  int device = -1;
+  cudaEvent_t ready = nullptr;  // recorded after the last device write
+  bool host_valid = false, dev_valid = false;
+  int exports = 0;              // live buffer views
+  size_t bytes() const { return (size_t)rows * cols * sizeof(float); }
+};
+
+static void mat_free_host(dcrf_mat* a) {
+  if (!a->host) return;
+  if (a->host_pinned)
+    g_pinned.put(a->host, a->bytes());
+  else
+    std::free(a->host);
+  a->host = nullptr;
+}
+static void mat_free_dev(dcrf_mat* a) {
+  if (a->dev) {
+    DeviceGuard g(a->device);
+    cudaFree(a->dev);
+    a->dev = nullptr;
+  }
+  if (a->ready) {
+    cudaEventDestroy(a->ready);
+    a->ready = nullptr;
+  }
+}
+
+// ---- model -------------------------------------------------------------------------------------
+struct Term {
+  Lattice lat;
+  float* norm = nullptr;  // [N]
+  int ntype = DCRF_NORMALIZE_SYMMETRIC;
+  int ckind = DCRF_COMPAT_POTTS;
+  float potts_w = 0.f;
+  float* diag = nullptr;  // Lp floats
+  float* Wm = nullptr;    // L*L floats, symmetrised
+  float *valA = nullptr, *valB = nullptr;  // (V+1) x Lp ping-pong value buffers
+  bool pre() const { return ntype == DCRF_NORMALIZE_SYMMETRIC || ntype == DCRF_NORMALIZE_BEFORE; }
+  bool post() const { return ntype == DCRF_NORMALIZE_SYMMETRIC || ntype == DCRF_NORMALIZE_AFTER; }
+};
+
+struct dcrf_model {
+  int N = 0, L = 0, W = 0, H = 0, device = 0;
+  RowLayout rl;
+  cudaStream_t stream = nullptr;
+  Profiler prof;
+  float* U = nullptr;  // N x Lp, null = no unary set
+  std::vector<Term*> terms;
+  float* acc = nullptr;  // staged path: running tmp1
+  float* msg = nullptr;  // staged path / KL: one message
+  double* kl_sums = nullptr;
+  int iter_mode = 0;
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
+  char* flush_buf = nullptr;
+  size_t flush_bytes = 0;
+  Ctx cx() { return Ctx{stream, &prof}; }
+};
+
+namespace {
+
+template <typename F>
+dcrf_status guarded(F&& f) {
+  try {
+    f();
+    return DCRF_OK;
+  } catch (const Error& e) {
+    g_last_error = e.what();
+    return e.code;
+  } catch (const std::bad_alloc&) {
+    g_last_error = "out of host memory";
+    return DCRF_ENOMEM;
+  } catch (const std::exception& e) {
+    g_last_error = e.what();
+    return DCRF_ECUDA;
+  }
+}
+
+int pick_device(int device) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    throw Error(DCRF_ECUDA, "no CUDA device available: libdcrf_b200 has no CPU path");
+  }
+  if (device < 0) {
+    const char* env = std::getenv("DCRF_B200_DEVICE");
+    device = env ? std::atoi(env) : 0;
+  }
+  DCRF_REQUIRE(device >= 0 && device < n, "device index " + std::to_string(device) + " out of range (" + std::to_string(n) + " visible)");
+  return device;
+}
+
+dcrf_model* model_new(int N, int L, int W, int H, int device) {
+  DCRF_REQUIRE(N >= 1, "need at least one variable");
+  DCRF_REQUIRE(L >= 1 && L <= 4096, "label count must be in [1, 4096]");
+  device = pick_device(device);
+  DCRF_CUDA(cudaSetDevice(device));
+  dcrf_model* m = new dcrf_model();
+  m->N = N, m->L = L, m->W = W, m->H = H, m->device = device;
+  m->rl = RowLayout(L);
+  DCRF_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+  cudaMemPool_t pool;
+  DCRF_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+  uint64_t keep = UINT64_MAX;  // keep freed blocks cached: no driver calls in steady state
+  DCRF_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  DCRF_CUDA(cudaEventCreate(&m->t0));
+  DCRF_CUDA(cudaEventCreate(&m->t1));
+  m->kl_sums = dev_alloc<double>(3, m->stream);
+  return m;
+}
+
+void term_free(dcrf_model* m, Term* t) {
+  cudaStream_t s = m->stream;
+  t->lat.release(s);
+  for (void* p : {(void*)t->norm, (void*)t->diag, (void*)t->Wm, (void*)t->valA, (void*)t->valB}) dev_free(p, s);
+  delete t;
+}
+
+void ensure_val(dcrf_model* m, Term* t) {
+  if (t->valA) return;
+  const size_t n = ((size_t)t->lat.V + 1) * m->rl.Lp;
+  t->valA = dev_alloc<float>(n, m->stream);
+  t->valB = dev_alloc<float>(n, m->stream);
+  // row 0 (absent neighbour) must read as zero forever; the kernels never write it
+  DCRF_CUDA(cudaMemsetAsync(t->valA, 0, n * sizeof(float), m->stream));
+  DCRF_CUDA(cudaMemsetAsync(t->valB, 0, n * sizeof(float), m->stream));
+}
+void ensure_scratch(dcrf_model* m) {
+  const size_t n = (size_t)m->N * m->rl.Lp;
+  if (!m->acc) m->acc = dev_alloc<float>(n, m->stream);
+  if (!m->msg) m->msg = dev_alloc<float>(n, m->stream);
+}
+
+// Permutohedral::compute: splat, d+1 blurs; returns the buffer holding the blurred vertex values
+const float* run_filter(Ctx cx, const Lattice& lt, RowLayout rl, const float* in, const float* pre_norm, float* A,
+                        float* B) {
+  launch_splat(cx, lt, rl, in, pre_norm, A);
+  float *src = A, *dst = B;
+  for (int j = 0; j <= lt.d; j++) {  // forward axis order: reverse=false everywhere on the inference path
+    launch_blur(cx, lt, rl, j, src, dst);
+    std::swap(src, dst);
+  }
+  return src;
+}
+
+bool can_fuse(dcrf_model* m) {
+  if (!fused_update_supported(m->rl) || (int)m->terms.size() > kMaxFusedTerms) return false;
+  for (Term* t : m->terms)
+    if (t->ckind == DCRF_COMPAT_MATRIX) return false;
+  return true;
+}
+
+CompatDev compat_of(const Term* t) {
+  CompatDev c;
+  c.kind = t->ckind;
+  c.neg_w = -t->potts_w;
+  c.diag = t->diag;
+  return c;
+}
+
+// message of term k for the current Q into `out` (mode as in launch_slice): PairwisePotential::apply
+void term_apply(dcrf_model* m, Term* t, const float* Q, int mode, bool neg_unary, float* out) {
+  Ctx cx = m->cx();
+  ensure_val(m, t);
+  const float* fin = run_filter(cx, t->lat, m->rl, Q, t->pre() ? t->norm : nullptr, t->valA, t->valB);
+  if (t->ckind != DCRF_COMPAT_MATRIX) {
+    CompatDev c = compat_of(t);
+    launch_slice(cx, t->lat, m->rl, fin, t->post() ? t->norm : nullptr, &c, mode, m->U, neg_unary, out);
+  } else {
+    ensure_scratch(m);
+    DCRF_REQUIRE(out != m->msg, "internal: matrix term needs msg as scratch");
+    launch_slice(cx, t->lat, m->rl, fin, t->post() ? t->norm : nullptr, nullptr, SLICE_WRITE, nullptr, false, m->msg);
+    launch_matrix_compat(cx, m->rl, m->N, t->Wm, m->msg, mode, m->U, neg_unary, out);
+  }
+}
+
+// one mean-field update of Q in place (the loop body of densecrf.cpp:122-129 / :187-200)
+void mf_step(dcrf_model* m, float* Q, bool neg_unary) {
+  Ctx cx = m->cx();
+  const bool fuse = m->iter_mode == 2 || (m->iter_mode == 0 && can_fuse(m));
+  if (fuse) {
+    DCRF_REQUIRE(can_fuse(m), "fused iteration not available for this model (matrix compatibility, >128 labels or >8 terms)");
+    FusedArgs a;
+    a.N = m->N;
+    a.nterms = (int)m->terms.size();
+    a.U = m->U;
+    a.neg_unary = neg_unary ? 1 : 0;
+    a.Q = Q;
+    for (int k = 0; k < a.nterms; k++) {
+      Term* t = m->terms[k];
+      ensure_val(m, t);
+      FusedTerm& ft = a.t[k];
+      ft.val = run_filter(cx, t->lat, m->rl, Q, t->pre() ? t->norm : nullptr, t->valA, t->valB);
+      ft.pix = t->lat.pix;
+      ft.post_norm = t->post() ? t->norm : nullptr;
+      ft.diag = t->diag;
+      ft.neg_w = -t->potts_w;
+      ft.alpha = t->lat.alpha;
+      ft.dp1 = t->lat.d + 1;
+      ft.ckind = t->ckind;
+    }
+    launch_fused_update(cx, m->rl, a);
+  } else {
+    ensure_scratch(m);
+    if (m->terms.empty()) launch_init_acc(cx, m->rl, m->N, m->U, neg_unary, m->acc);
+    for (size_t k = 0; k < m->terms.size(); k++)
+      term_apply(m, m->terms[k], Q, k == 0 ? SLICE_ACC_FIRST : SLICE_ACC_NEXT, neg_unary, m->acc);
+    launch_softmax(cx, m->rl, m->N, m->acc, Q);
+  }
+}
+
+// Q0 = expAndNormalize(-unary) (densecrf.cpp:120)
+void mf_init(dcrf_model* m, float* Q) {
+  Ctx cx = m->cx();
+  if (m->iter_mode != 1 && fused_update_supported(m->rl)) {
+    FusedArgs a;
+    a.N = m->N, a.nterms = 0, a.U = m->U, a.neg_unary = 1, a.Q = Q;
+    launch_fused_update(cx, m->rl, a);
+  } else {
+    ensure_scratch(m);
+    launch_init_acc(cx, m->rl, m->N, m->U, true, m->acc);
+    launch_softmax(cx, m->rl, m->N, m->acc, Q);
+  }
+}
+
+void mat_reset(dcrf_mat* a, int rows, int cols) {
+  if (a->rows == rows && a->cols == cols) return;
+  DCRF_REQUIRE(a->exports == 0, "cannot resize a matrix while a buffer view of it is alive");
+  mat_free_host(a);
+  mat_free_dev(a);
+  a->rows = rows, a->cols = cols;
+  a->host_valid = a->dev_valid = false;
+}
+
+// make sure `a` has a device buffer of this model's layout holding its current contents
+float* mat_device(dcrf_model* m, dcrf_mat* a, bool need_contents) {
+  DCRF_REQUIRE(a->rows == m->L && a->cols == m->N,
+               "matrix has shape (" + std::to_string(a->rows) + ", " + std::to_string(a->cols) + "), model needs (" +
+                   std::to_string(m->L) + ", " + std::to_string(m->N) + ")");
+  if (a->dev && a->device != m->device) {
+    if (!a->host_valid && a->dev_valid) throw Error(DCRF_EINVAL, "matrix lives on another device");
+    mat_free_dev(a);
+    a->dev_valid = false;
+  }
+  const size_t n = (size_t)m->N * m->rl.Lp;
+  if (!a->dev) {
+    DCRF_CUDA(cudaMalloc(&a->dev, n * sizeof(float)));
+    a->device = m->device;
+    a->dev_valid = false;
+  }
+  if (!a->ready) DCRF_CUDA(cudaEventCreateWithFlags(&a->ready, cudaEventDisableTiming));
+  if (need_contents && !a->dev_valid) {
+    DCRF_REQUIRE(a->host && a->host_valid, "matrix has no contents");
+    float* stage = dev_alloc<float>((size_t)m->N * m->L, m->stream);
+    DCRF_CUDA(cudaMemcpyAsync(stage, a->host, a->bytes(), cudaMemcpyHostToDevice, m->stream));
+    launch_unpack_rows(m->cx(), m->rl, m->N, stage, a->dev);
+    dev_free(stage, m->stream);
+    a->dev_valid = true;
+  }
+  return a->dev;
+}
+
+// the device copy was just rewritten on the model's stream
+void mat_written(dcrf_model* m, dcrf_mat* a);
+
+void mat_download(dcrf_mat* a, cudaStream_t s, Profiler* prof) {
+  // pack rows (cols x Lp) -> col-major rows*cols on the device, then one contiguous D2H copy
+  DeviceGuard g(a->device);
+  RowLayout rl(a->rows);
+  if (!a->host) {
+    a->host = (float*)g_pinned.get(a->bytes());
+    a->host_pinned = true;
+  }
+  float* stage = dev_alloc<float>((size_t)a->rows * a->cols, s);
+  launch_pack_rows(Ctx{s, prof}, rl, a->cols, a->dev, stage);
+  DCRF_CUDA(cudaMemcpyAsync(a->host, stage, a->bytes(), cudaMemcpyDeviceToHost, s));
+  dev_free(stage, s);
+  DCRF_CUDA(cudaStreamSynchronize(s));
+  a->host_valid = true;
+}
+
+void mat_written(dcrf_model* m, dcrf_mat* a) {
+  a->dev_valid = true;
+  a->host_valid = false;
+  DCRF_CUDA(cudaEventRecord(a->ready, m->stream));
+  if (a->exports > 0) {  // a live numpy view must observe the update, like the reference's shared Eigen memory
+    mat_download(a, m->stream, &m->prof);
+    a->dev_valid = false;  // ...and may be written through before the next call
+  }
+}
+
+float* upload_tmp(dcrf_model* m, const void* host, size_t bytes) {
+  char* d = dev_alloc<char>(bytes, m->stream);
+  DCRF_CUDA(cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, m->stream));
+  return (float*)d;
+}
+
+void add_term(dcrf_model* m, const FeatureSource& src, int d, int compat_kind, const float* compat, int ktype,
+              int ntype) {
+  DCRF_REQUIRE(ntype >= 0 && ntype <= 3, "bad NormalizationType");
+  DCRF_REQUIRE(ktype >= 0 && ktype <= 2, "bad KernelType");  // no effect on inference (pairwise.cpp:116-121)
+  DCRF_REQUIRE(compat_kind >= 0 && compat_kind <= 2 && compat, "bad label compatibility");
+  Ctx cx = m->cx();
+  cudaStream_t s = m->stream;
+  Term* t = new Term();
+  try {
+    lattice_build(cx, src, d, m->N, &t->lat);
+    t->ntype = ntype;
+    t->ckind = compat_kind;
+    const int L = m->L, Lp = m->rl.Lp;
+    if (compat_kind == DCRF_COMPAT_POTTS) {
+      t->potts_w = compat[0];
+    } else if (compat_kind == DCRF_COMPAT_DIAGONAL) {
+      std::vector<float> w(Lp, 0.f);
+      std::copy(compat, compat + L, w.begin());
+      t->diag = dev_alloc<float>(Lp, s);
+      DCRF_CUDA(cudaMemcpyAsync(t->diag, w.data(), Lp * sizeof(float), cudaMemcpyHostToDevice, s));
+      DCRF_CUDA(cudaStreamSynchronize(s));
+    } else {
+      std::vector<float> w((size_t)L * L);
+      for (int a = 0; a < L; a++)
+        for (int b = 0; b < L; b++) w[(size_t)a * L + b] = 0.5f * (compat[(size_t)a * L + b] + compat[(size_t)b * L + a]);
+      t->Wm = dev_alloc<float>((size_t)L * L, s);
+      DCRF_CUDA(cudaMemcpyAsync(t->Wm, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+      DCRF_CUDA(cudaStreamSynchronize(s));
+    }
+    // norm_ = lattice_.compute(ones)  (pairwise.cpp:44): a 1-label pass, which takes the seqCompute arithmetic
+    const int N = m->N;
+    RowLayout r1(1);
+    float* ones = dev_alloc<float>(N, s);
+    launch_fill(cx, ones, N, 1.0f);
+    float* A = dev_alloc<float>((size_t)t->lat.V + 1, s);
+    float* B = dev_alloc<float>((size_t)t->lat.V + 1, s);
+    DCRF_CUDA(cudaMemsetAsync(A, 0, ((size_t)t->lat.V + 1) * sizeof(float), s));
+    DCRF_CUDA(cudaMemsetAsync(B, 0, ((size_t)t->lat.V + 1) * sizeof(float), s));
+    const float* fin = run_filter(cx, t->lat, r1, ones, nullptr, A, B);
+    t->norm = dev_alloc<float>(N, s);
+    launch_slice(cx, t->lat, r1, fin, nullptr, nullptr, SLICE_WRITE, nullptr, false, t->norm);
+    if (ntype == DCRF_NO_NORMALIZATION) {
+      // mean_norm = N / sum(norm): the reference adds N floats one after the other in float
+      // (pairwise.cpp:47-51); that rounding sequence is inherently serial, so it runs on the host once
+      std::vector<float> h(N);
+      DCRF_CUDA(cudaMemcpyAsync(h.data(), t->norm, (size_t)N * sizeof(float), cudaMemcpyDeviceToHost, s));
+      DCRF_CUDA(cudaStreamSynchronize(s));
+      float mean = 0.f;
+      for (int i = 0; i < N; i++) mean += h[i];
+      mean = (float)N / mean;
+      launch_fill(cx, t->norm, N, mean);
+    } else {
+      launch_norm_transform(cx, N, t->norm, ntype == DCRF_NORMALIZE_SYMMETRIC);
+    }
+    dev_free(ones, s);
+    dev_free(A, s);
+    dev_free(B, s);
+    DCRF_CUDA(cudaGetLastError());
+    DCRF_CUDA(cudaStreamSynchronize(s));
+  } catch (...) {
+    term_free(m, t);
+    throw;
+  }
+  m->terms.push_back(t);
+}
+
+dcrf_mat* new_result_mat(dcrf_model* m) {
+  dcrf_mat* a = new dcrf_mat();
+  a->rows = m->L, a->cols = m->N;
+  return a;
+}
+
+}  // namespace
+
+// =================================================================================================
+// C-ABI
+// =================================================================================================
+extern "C" {
+
+const char* dcrf_last_error(void) { return g_last_error.c_str(); }
+int dcrf_abi_version(void) { return DCRF_ABI_VERSION; }
+int dcrf_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+dcrf_status dcrf_create(int nvar, int nlabels, int device, dcrf_t** out) {
+  return guarded([&] {
+    DCRF_REQUIRE(out, "null output pointer");
+    *out = model_new(nvar, nlabels, 0, 0, device);
+  });
+}
+dcrf_status dcrf_create_2d(int width, int height, int nlabels, int device, dcrf_t** out) {
+  return guarded([&] {
+    DCRF_REQUIRE(out, "null output pointer");
+    DCRF_REQUIRE(width >= 1 && height >= 1, "width and height must be positive");
+    DCRF_REQUIRE((int64_t)width * height < (1ll << 31), "image too large");
+    *out = model_new(width * height, nlabels, width, height, device);
+  });
+}
+void dcrf_destroy(dcrf_t* m) {
+  if (!m) return;
+  try {
+    DeviceGuard g(m->device);
+    cudaStreamSynchronize(m->stream);
+    for (Term* t : m->terms) term_free(m, t);
+    for (void* p : {(void*)m->U, (void*)m->acc, (void*)m->msg, (void*)m->kl_sums, (void*)m->flush_buf}) dev_free(p, m->stream);
+    cudaStreamSynchronize(m->stream);
+    m->prof.destroy();
+    cudaEventDestroy(m->t0);
+    cudaEventDestroy(m->t1);
+    cudaStreamDestroy(m->stream);
+  } catch (...) {
+  }
+  delete m;
+}
+
+dcrf_status dcrf_set_unary_const(dcrf_t* m, const float* u_LxN) {
+  return guarded([&] {
+    DCRF_REQUIRE(m && u_LxN, "null argument");
+    DeviceGuard g(m->device);
+    const size_t n = (size_t)m->N * m->L;
+    float* planes = upload_tmp(m, u_LxN, n * sizeof(float));
+    if (!m->U) m->U = dev_alloc<float>((size_t)m->N * m->rl.Lp, m->stream);
+    launch_planes_to_rows(m->cx(), m->rl, m->N, planes, m->U);
+    dev_free(planes, m->stream);
+    DCRF_CUDA(cudaGetLastError());
+    DCRF_CUDA(cudaStreamSynchronize(m->stream));  // the caller may free/overwrite u now
+  });
+}
+dcrf_status dcrf_set_unary_logistic(dcrf_t* m, const float* Lmat_LxF, int F, const float* f_FxN) {
+  return guarded([&] {
+    DCRF_REQUIRE(m && Lmat_LxF && f_FxN && F >= 1, "bad argument");
+    DeviceGuard g(m->device);
+    float* dL = upload_tmp(m, Lmat_LxF, (size_t)m->L * F * sizeof(float));
+    float* df = upload_tmp(m, f_FxN, (size_t)F * m->N * sizeof(float));
+    if (!m->U) m->U = dev_alloc<float>((size_t)m->N * m->rl.Lp, m->stream);
+    launch_logistic_unary(m->cx(), m->rl, m->N, F, dL, df, m->U);
+    dev_free(dL, m->stream);
+    dev_free(df, m->stream);
+    DCRF_CUDA(cudaGetLastError());
+    DCRF_CUDA(cudaStreamSynchronize(m->stream));
+  });
+}
+
+dcrf_status dcrf_add_pairwise_energy(dcrf_t* m, const float* feat_dxN, int d, int compat_kind, const float* compat_data,
+                                     int kernel_type, int norm_type) {
+  return guarded([&] {
+    DCRF_REQUIRE(m && feat_dxN, "null argument");
+    DCRF_REQUIRE(d >= 1 && d <= kMaxFeatureDims, "feature dimension must be in [1, 32]");
+    DeviceGuard g(m->device);
+    float* f = upload_tmp(m, feat_dxN, (size_t)d * m->N * sizeof(float));
+    FeatureSource src{};
+    src.kind = FEAT_GENERIC;
+    src.feat = f;
+    try {
+      add_term(m, src, d, compat_kind, compat_data, kernel_type, norm_type);
+    } catch (...) {
+      dev_free(f, m->stream);
+      throw;
+    }
+    dev_free(f, m->stream);
+  });
+}
+dcrf_status dcrf_add_pairwise_gaussian(dcrf_t* m, float sx, float sy, int compat_kind, const float* compat_data,
+                                       int kernel_type, int norm_type) {
+  return guarded([&] {
+    DCRF_REQUIRE(m, "null argument");
+    DCRF_REQUIRE(m->W > 0, "addPairwiseGaussian needs a 2D model (dcrf_create_2d)");
+    DeviceGuard g(m->device);
+    FeatureSource src{};
+    src.kind = FEAT_GAUSS2D;
+    src.W = m->W;
+    src.s[0] = sx, src.s[1] = sy;
+    add_term(m, src, 2, compat_kind, compat_data, kernel_type, norm_type);
+  });
+}
+dcrf_status dcrf_add_pairwise_bilateral(dcrf_t* m, float sx, float sy, float sr, float sg, float sb,
+                                        const uint8_t* rgb_HxWx3, int compat_kind, const float* compat_data,
+                                        int kernel_type, int norm_type) {
+  return guarded([&] {
+    DCRF_REQUIRE(m && rgb_HxWx3, "null argument");
+    DCRF_REQUIRE(m->W > 0, "addPairwiseBilateral needs a 2D model (dcrf_create_2d)");
+    DeviceGuard g(m->device);
+    uint8_t* im = (uint8_t*)upload_tmp(m, rgb_HxWx3, (size_t)m->N * 3);
+    FeatureSource src{};
+    src.kind = FEAT_BILATERAL2D;
+    src.W = m->W;
+    src.rgb = im;
+    src.s[0] = sx, src.s[1] = sy, src.s[2] = sr, src.s[3] = sg, src.s[4] = sb;
+    try {
+      add_term(m, src, 5, compat_kind, compat_data, kernel_type, norm_type);
+    } catch (...) {
+      dev_free(im, m->stream);
+      throw;
+    }
+    dev_free(im, m->stream);
+  });
+}
+
+dcrf_status dcrf_inference_into(dcrf_t* m, int n_iterations, dcrf_mat_t* Q) {
+  return guarded([&] {
+    DCRF_REQUIRE(m && Q, "null argument");
+    DCRF_REQUIRE(n_iterations >= 0, "negative iteration count");
+    DeviceGuard g(m->device);
+    mat_reset(Q, m->L, m->N);
+    float* q = mat_device(m, Q, false);
+    mf_init(m, q);
+    for (int it = 0; it < n_iterations; it++) mf_step(m, q, true);
+    DCRF_CUDA(cudaGetLastError());
+    mat_written(m, Q);
+  });
+}
+dcrf_status dcrf_inference(dcrf_t* m, int n_iterations, dcrf_mat_t** Q) {
+  if (!m || !Q) {
+    g_last_error = "null argument";
+    return DCRF_EINVAL;
+  }
+  dcrf_mat* a = new dcrf_mat();
+  dcrf_status st = dcrf_inference_into(m, n_iterations, a);
+  if (st != DCRF_OK) {
+    dcrf_mat_destroy(a);
+    return st;
+  }
+  *Q = a;
+  return DCRF_OK;
+}
+dcrf_status dcrf_start_inference(dcrf_t* m, dcrf_mat_t** Q) {
+  if (!m || !Q) {
+    g_last_error = "null argument";
+    return DCRF_EINVAL;
+  }
+  dcrf_mat* a = nullptr;
+  dcrf_status st = guarded([&] {
+    DeviceGuard g(m->device);
+    a = new_result_mat(m);
+    float* q = mat_device(m, a, false);
+    if (m->U)
+      mf_init(m, q);
+    else  // startInference without a unary leaves Q all-zero (densecrf.cpp:178-186)
+      DCRF_CUDA(cudaMemsetAsync(q, 0, (size_t)m->N * m->rl.Lp * sizeof(float), m->stream));
+    DCRF_CUDA(cudaGetLastError());
+    mat_written(m, a);
+  });
+  if (st != DCRF_OK) {
+    dcrf_mat_destroy(a);
+    return st;
+  }
+  *Q = a;
+  return DCRF_OK;
+}
+dcrf_status dcrf_step_inference(dcrf_t* m, dcrf_mat_t* Q, dcrf_mat_t* tmp1, dcrf_mat_t* tmp2) {
+  (void)tmp1;
+  (void)tmp2;
+  return guarded([&] {
+    DCRF_REQUIRE(m && Q, "null argument");
+    DeviceGuard g(m->device);
+    float* q = mat_device(m, Q, true);
+    mf_step(m, q, false);
+    DCRF_CUDA(cudaGetLastError());
+    mat_written(m, Q);
+  });
+}
+dcrf_status dcrf_kl_divergence(dcrf_t* m, dcrf_mat_t* Q, double* out) {
+  return guarded([&] {
+    DCRF_REQUIRE(m && Q && out, "null argument");
+    DeviceGuard g(m->device);
+    Ctx cx = m->cx();
+    float* q = mat_device(m, Q, true);
+    ensure_scratch(m);
+    DCRF_CUDA(cudaMemsetAsync(m->kl_sums, 0, 3 * sizeof(double), m->stream));
+    launch_kl_terms(cx, m->rl, m->N, q, m->U, nullptr, m->kl_sums);
+    for (Term* t : m->terms) {
+      term_apply(m, t, q, SLICE_WRITE, false, m->acc);
+      launch_kl_terms(cx, m->rl, m->N, q, nullptr, m->acc, m->kl_sums);
+    }
+    double h[3];
+    DCRF_CUDA(cudaMemcpyAsync(h, m->kl_sums, sizeof(h), cudaMemcpyDeviceToHost, m->stream));
+    DCRF_CUDA(cudaStreamSynchronize(m->stream));
+    *out = h[0] + h[1] + h[2];
+  });
+}
+dcrf_status dcrf_current_map(dcrf_t* m, dcrf_mat_t* Q, int16_t* labels_N) {
+  return guarded([&] {
+    DCRF_REQUIRE(m && Q && labels_N, "null argument");
+    DeviceGuard g(m->device);
+    float* q = mat_device(m, Q, true);
+    int16_t* d = dev_alloc<int16_t>(m->N, m->stream);
+    launch_argmax(m->cx(), m->rl, m->N, q, d);
+    DCRF_CUDA(cudaMemcpyAsync(labels_N, d, (size_t)m->N * sizeof(int16_t), cudaMemcpyDeviceToHost, m->stream));
+    dev_free(d, m->stream);
+    DCRF_CUDA(cudaStreamSynchronize(m->stream));
+  });
+}
+
+// ---- matrices ------------------------------------------------------------------------------------
+dcrf_status dcrf_mat_create_empty(dcrf_mat_t** out) {
+  return guarded([&] {
+    DCRF_REQUIRE(out, "null output pointer");
+    *out = new dcrf_mat();
+  });
+}
+dcrf_status dcrf_mat_from_host(const float* rowmajor, int rows, int cols, dcrf_mat_t** out) {
+  return guarded([&] {
+    DCRF_REQUIRE(out && rows >= 0 && cols >= 0 && (rowmajor || rows * cols == 0), "bad argument");
+    dcrf_mat* a = new dcrf_mat();
+    a->rows = rows, a->cols = cols;
+    a->host = (float*)std::malloc(std::max<size_t>(a->bytes(), 4));
+    if (!a->host) {
+      delete a;
+      throw std::bad_alloc();
+    }
+    for (int r = 0; r < rows; r++)
+      for (int c = 0; c < cols; c++) a->host[(size_t)c * rows + r] = rowmajor[(size_t)r * cols + c];
+    a->host_valid = true;
+    *out = a;
+  });
+}
+dcrf_status dcrf_vec_from_host(const float* data, int n, dcrf_mat_t** out) { return dcrf_mat_from_host(data, n, 1, out); }
+void dcrf_mat_destroy(dcrf_mat_t* a) {
+  if (!a) return;
+  try {
+    mat_free_dev(a);
+  } catch (...) {
+  }
+  mat_free_host(a);
+  delete a;
+}
+int dcrf_mat_rows(const dcrf_mat_t* a) { return a ? a->rows : 0; }
+int dcrf_mat_cols(const dcrf_mat_t* a) { return a ? a->cols : 0; }
+dcrf_status dcrf_mat_host_ptr(dcrf_mat_t* a, float** ptr) {
+  return guarded([&] {
+    DCRF_REQUIRE(a && ptr, "null argument");
+    if (!a->host_valid && a->dev_valid) {
+      DeviceGuard g(a->device);
+      // order after the producer without needing its stream: wait on the matrix' own event
+      cudaStream_t s;
+      DCRF_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+      try {
+        DCRF_CUDA(cudaStreamWaitEvent(s, a->ready, 0));
+        Profiler none;
+        mat_download(a, s, &none);
+      } catch (...) {
+        cudaStreamDestroy(s);
+        throw;
+      }
+      cudaStreamDestroy(s);
+    }
+    if (!a->host) {  // empty 0x0 matrix or never written
+      a->host = (float*)std::calloc(std::max<size_t>((size_t)a->rows * a->cols, 1), sizeof(float));
+      a->host_valid = true;
+    }
+    a->exports++;
+    *ptr = a->host;
+  });
+}
+void dcrf_mat_release_host(dcrf_mat_t* a) {
+  if (!a || a->exports <= 0) return;
+  a->exports--;
+  // the view was writable (readonly=0 in the reference's buffer, eigen.pyx:40,92): assume it was written
+  a->dev_valid = false;
+  a->host_valid = true;
+}
+
+// ---- measurement -----------------------------------------------------------------------------------
+dcrf_status dcrf_synchronize(dcrf_t* m) {
+  return guarded([&] {
+    DCRF_REQUIRE(m, "null argument");
+    DeviceGuard g(m->device);
+    DCRF_CUDA(cudaStreamSynchronize(m->stream));
+  });
+}
+dcrf_status dcrf_timer_start(dcrf_t* m) {
+  return guarded([&] {
+    DCRF_REQUIRE(m, "null argument");
+    DeviceGuard g(m->device);
+    DCRF_CUDA(cudaEventRecord(m->t0, m->stream));
+  });
+}
+dcrf_status dcrf_timer_stop(dcrf_t* m, float* ms) {
+  return guarded([&] {
+    DCRF_REQUIRE(m && ms, "null argument");
+    DeviceGuard g(m->device);
+    DCRF_CUDA(cudaEventRecord(m->t1, m->stream));
+    DCRF_CUDA(cudaEventSynchronize(m->t1));
+    DCRF_CUDA(cudaEventElapsedTime(ms, m->t0, m->t1));
+  });
+}
+dcrf_status dcrf_profile_enable(dcrf_t* m, int on) {
+  return guarded([&] {
+    DCRF_REQUIRE(m, "null argument");
+    DeviceGuard g(m->device);
+    DCRF_CUDA(cudaStreamSynchronize(m->stream));
+    m->prof.collect();
+    m->prof.enabled = on != 0;
+  });
+}
+dcrf_status dcrf_profile_read(dcrf_t* m, dcrf_prof_entry* out, int cap, int* n, int reset) {
+  return guarded([&] {
+    DCRF_REQUIRE(m && n, "null argument");
+    DeviceGuard g(m->device);
+    DCRF_CUDA(cudaStreamSynchronize(m->stream));
+    m->prof.collect();
+    int k = 0;
+    for (auto& r : m->prof.recs) {
+      if (out && k < cap) {
+        std::memset(&out[k], 0, sizeof(out[k]));
+        std::strncpy(out[k].name, r.name.c_str(), sizeof(out[k].name) - 1);
+        out[k].launches = r.launches;
+        out[k].ms_total = r.ms;
+      }
+      k++;
+      if (reset) r.launches = 0, r.ms = 0.f;
+    }
+    *n = k;
+  });
+}
+int64_t dcrf_launch_count(const dcrf_t* m) { return m ? m->prof.launches : 0; }
+dcrf_status dcrf_flush_l2(dcrf_t* m) {
+  return guarded([&] {
+    DCRF_REQUIRE(m, "null argument");
+    DeviceGuard g(m->device);
+    if (!m->flush_buf) {
+      m->flush_bytes = 256ull << 20;  // 2x the 126 MB L2
+      m->flush_buf = dev_alloc<char>(m->flush_bytes, m->stream);
+    }
+    m->prof.launches++;
+    DCRF_CUDA(cudaMemsetAsync(m->flush_buf, 0x5a, m->flush_bytes, m->stream));
+  });
+}
+
+// ---- introspection -----------------------------------------------------------------------------------
+int dcrf_num_pairwise(const dcrf_t* m) { return m ? (int)m->terms.size() : 0; }
+dcrf_status dcrf_lattice_info(const dcrf_t* m, int k, int* d, int* N, int* V) {
+  return guarded([&] {
+    DCRF_REQUIRE(m && k >= 0 && k < (int)m->terms.size(), "no such pairwise term");
+    const Lattice& lt = m->terms[k]->lat;
+    if (d) *d = lt.d;
+    if (N) *N = lt.N;
+    if (V) *V = lt.V;
+  });
+}
+dcrf_status dcrf_lattice_dump(dcrf_t* m, int k, int32_t* offset, float* bary, int16_t* keys, int32_t* nbr, float* norm) {
+  return guarded([&] {
+    DCRF_REQUIRE(m && k >= 0 && k < (int)m->terms.size(), "no such pairwise term");
+    DeviceGuard g(m->device);
+    const Term* t = m->terms[k];
+    const Lattice& lt = t->lat;
+    cudaStream_t s = m->stream;
+    const size_t E = (size_t)lt.E;
+    if (offset || bary) {
+      std::vector<PixEntry> h(E);
+      DCRF_CUDA(cudaMemcpyAsync(h.data(), lt.pix, E * sizeof(PixEntry), cudaMemcpyDeviceToHost, s));
+      DCRF_CUDA(cudaStreamSynchronize(s));
+      for (size_t e = 0; e < E; e++) {
+        if (offset) offset[e] = h[e].row - 1;
+        if (bary) bary[e] = h[e].w;
+      }
+    }
+    if (keys) DCRF_CUDA(cudaMemcpyAsync(keys, lt.keys, (size_t)lt.V * lt.d * sizeof(int16_t), cudaMemcpyDeviceToHost, s));
+    if (nbr) {
+      const size_t n = (size_t)lt.V * (lt.d + 1);
+      std::vector<int2> h(n);
+      DCRF_CUDA(cudaMemcpyAsync(h.data(), lt.nbr, n * sizeof(int2), cudaMemcpyDeviceToHost, s));
+      DCRF_CUDA(cudaStreamSynchronize(s));
+      for (size_t e = 0; e < n; e++) nbr[2 * e] = h[e].x - 1, nbr[2 * e + 1] = h[e].y - 1;
+    }
+    if (norm) DCRF_CUDA(cudaMemcpyAsync(norm, t->norm, (size_t)lt.N * sizeof(float), cudaMemcpyDeviceToHost, s));
+    DCRF_CUDA(cudaStreamSynchronize(s));
+  });
+}
+dcrf_status dcrf_lattice_filter(dcrf_t* m, int k, const float* in_NxL, int L, float* out_NxL) {
+  return guarded([&] {
+    DCRF_REQUIRE(m && k >= 0 && k < (int)m->terms.size(), "no such pairwise term");
+    DCRF_REQUIRE(in_NxL && out_NxL && L >= 1 && L <= 4096, "bad argument");
+    DeviceGuard g(m->device);
+    Ctx cx = m->cx();
+    cudaStream_t s = m->stream;
+    const Lattice& lt = m->terms[k]->lat;
+    RowLayout rl(L);
+    const int N = lt.N;
+    float* packed = upload_tmp(m, in_NxL, (size_t)N * L * sizeof(float));
+    float* rows = dev_alloc<float>((size_t)N * rl.Lp, s);
+    launch_unpack_rows(cx, rl, N, packed, rows);
+    const size_t vn = ((size_t)lt.V + 1) * rl.Lp;
+    float* A = dev_alloc<float>(vn, s);
+    float* B = dev_alloc<float>(vn, s);
+    DCRF_CUDA(cudaMemsetAsync(A, 0, vn * sizeof(float), s));
+    DCRF_CUDA(cudaMemsetAsync(B, 0, vn * sizeof(float), s));
+    const float* fin = run_filter(cx, lt, rl, rows, nullptr, A, B);
+    launch_slice(cx, lt, rl, fin, nullptr, nullptr, SLICE_WRITE, nullptr, false, rows);
+    launch_pack_rows(cx, rl, N, rows, packed);
+    DCRF_CUDA(cudaMemcpyAsync(out_NxL, packed, (size_t)N * L * sizeof(float), cudaMemcpyDeviceToHost, s));
+    for (void* p : {(void*)packed, (void*)rows, (void*)A, (void*)B}) dev_free(p, s);
+    DCRF_CUDA(cudaGetLastError());
+    DCRF_CUDA(cudaStreamSynchronize(s));
+  });
+}
+dcrf_status dcrf_pairwise_apply(dcrf_t* m, int k, dcrf_mat_t* Q, dcrf_mat_t** out) {
+  if (!out) {
+    g_last_error = "null argument";
+    return DCRF_EINVAL;
+  }
+  dcrf_mat* a = nullptr;
+  dcrf_status st = guarded([&] {
+    DCRF_REQUIRE(m && Q && k >= 0 && k < (int)m->terms.size(), "no such pairwise term");
+    DeviceGuard g(m->device);
+    float* q = mat_device(m, Q, true);
+    a = new_result_mat(m);
+    float* o = mat_device(m, a, false);
+    term_apply(m, m->terms[k], q, SLICE_WRITE, false, o);
+    DCRF_CUDA(cudaGetLastError());
+    mat_written(m, a);
+  });
+  if (st != DCRF_OK) {
+    dcrf_mat_destroy(a);
+    return st;
+  }
+  *out = a;
+  return DCRF_OK;
+}
+dcrf_status dcrf_set_iteration_mode(dcrf_t* m, int mode) {
+  return guarded([&] {
+    DCRF_REQUIRE(m && mode >= 0 && mode <= 2, "bad iteration mode");
+    m->iter_mode = mode;
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,213 @@
+// Internal declarations shared by the .cu files of libdcrf_b200.so.  Not part of the C-ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/dcrf_b200.h"
+
+namespace dcrf {
+
+// ---------------------------------------------------------------------------------------------
+// errors: internal code throws, the extern "C" layer converts to dcrf_status + dcrf_last_error()
+// ---------------------------------------------------------------------------------------------
+struct Error : public std::runtime_error {
+  dcrf_status code;
+  Error(dcrf_status c, const std::string& what) : std::runtime_error(what), code(c) {}
+};
+[[noreturn]] void fail_cuda(cudaError_t e, const char* expr, const char* file, int line);
+#define DCRF_CUDA(expr)                                                  \
+  do {                                                                   \
+    cudaError_t _e = (expr);                                             \
+    if (_e != cudaSuccess) ::dcrf::fail_cuda(_e, #expr, __FILE__, __LINE__); \
+  } while (0)
+#define DCRF_REQUIRE(cond, msg)                                          \
+  do {                                                                   \
+    if (!(cond)) throw ::dcrf::Error(DCRF_EINVAL, (msg));                \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// row layout of every per-pixel / per-vertex value buffer: the L labels of a row are contiguous and
+// padded to a whole number of vector chunks, so one row is C aligned chunks of VEC floats.
+//   L == 1 -> VEC 1;  L == 2 -> VEC 2;  L >= 3 -> VEC 4 (float4 rows, Lp = ceil4(L))
+// ---------------------------------------------------------------------------------------------
+struct RowLayout {
+  int L, Lp, vec, C;
+  explicit RowLayout(int L_ = 1) : L(L_) {
+    vec = (L_ <= 1) ? 1 : (L_ == 2 ? 2 : 4);
+    C = (L_ + vec - 1) / vec;
+    Lp = C * vec;
+  }
+  // L<=2 takes the reference's seqCompute arithmetic, otherwise sseCompute (permutohedral.cpp:596-604)
+  bool seq() const { return L <= 2; }
+};
+
+// stream-ordered device memory (cudaMallocAsync pool with unlimited retention: steady-state
+// allocations inside inference cost no driver call)
+template <typename T>
+T* dev_alloc(size_t n, cudaStream_t s) {
+  void* p = nullptr;
+  if (n == 0) n = 1;
+  cudaError_t e = cudaMallocAsync(&p, n * sizeof(T), s);
+  if (e == cudaErrorMemoryAllocation) {
+    cudaGetLastError();
+    throw Error(DCRF_ENOMEM, "out of device memory allocating " + std::to_string(n * sizeof(T)) + " bytes");
+  }
+  if (e != cudaSuccess) fail_cuda(e, "cudaMallocAsync", __FILE__, __LINE__);
+  return static_cast<T*>(p);
+}
+inline void dev_free(void* p, cudaStream_t s) {
+  if (p) cudaFreeAsync(p, s);
+}
+
+// per-kernel-class profiling / launch accounting, owned by the model
+struct Profiler {
+  struct Rec {
+    std::string name;
+    int launches = 0;
+    float ms = 0.f;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+  };
+  bool enabled = false;
+  int64_t launches = 0;
+  std::vector<Rec> recs;
+  std::vector<cudaEvent_t> free_events;
+  cudaEvent_t get_event();
+  int index_of(const char* name);
+  void collect();  // requires the stream to be idle
+  void destroy();
+};
+
+// RAII bracket around one kernel launch
+struct LaunchScope {
+  Profiler* p;
+  cudaStream_t s;
+  int idx = -1;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  LaunchScope(Profiler* prof, cudaStream_t st, const char* name) : p(prof), s(st) {
+    p->launches++;
+    if (p->enabled) {
+      idx = p->index_of(name);
+      e0 = p->get_event();
+      e1 = p->get_event();
+      cudaEventRecord(e0, s);
+    }
+  }
+  ~LaunchScope() {
+    if (idx >= 0) {
+      cudaEventRecord(e1, s);
+      p->recs[idx].pending.emplace_back(e0, e1);
+      p->recs[idx].launches++;
+    }
+  }
+};
+
+struct Ctx {  // what every launcher needs
+  cudaStream_t stream;
+  Profiler* prof;
+};
+
+// ---------------------------------------------------------------------------------------------
+// lattice (lattice.cu)
+// ---------------------------------------------------------------------------------------------
+struct PixEntry {  // one corner of a pixel's enclosing simplex
+  int row;         // vertex id + 1 (row 0 of a value buffer is the all-zero "absent" row)
+  float w;         // barycentric weight
+};
+struct CsrEntry {  // one contribution to a vertex, rows sorted by (pixel, corner) ascending
+  int pix;
+  float w;
+};
+
+enum FeatureKind { FEAT_GENERIC = 0, FEAT_GAUSS2D = 1, FEAT_BILATERAL2D = 2 };
+struct FeatureSource {
+  int kind;
+  const float* feat;  // device, d x N row-major (FEAT_GENERIC)
+  const uint8_t* rgb; // device, N x 3 (FEAT_BILATERAL2D)
+  int W;
+  float s[5];         // sx, sy, sr, sg, sb
+};
+
+struct Lattice {
+  int N = 0, d = 0, V = 0, Npad = 0;
+  int64_t E = 0;               // N*(d+1) contributions
+  PixEntry* pix = nullptr;     // [N*(d+1)]
+  int* csr_start = nullptr;    // [V+1]
+  CsrEntry* csr = nullptr;     // [E]
+  int2* nbr = nullptr;         // [(d+1)*V] rows (id+1) of the -/+ neighbours, 0 = absent
+  int16_t* keys = nullptr;     // [V*d]
+  float alpha = 1.f;           // 1/(1+2^-d)
+  int max_row = 0;             // longest CSR row (diagnostic)
+  void release(cudaStream_t s);
+};
+
+static const int kMaxFeatureDims = 32;
+void lattice_build(Ctx cx, const FeatureSource& src, int d, int N, Lattice* out);
+
+// ---------------------------------------------------------------------------------------------
+// filter / update kernels (filter.cu)
+// ---------------------------------------------------------------------------------------------
+// out rows (V+1) x Lp.  `in` is N x Lp; pre_norm (may be null) scales row i by norm[i] first.
+void launch_splat(Ctx cx, const Lattice& lt, RowLayout rl, const float* in, const float* pre_norm, float* val);
+// one Jacobi blur pass along axis j: dst = src + 0.5*(src[n1] + src[n2])
+void launch_blur(Ctx cx, const Lattice& lt, RowLayout rl, int axis, const float* src, float* dst);
+
+enum SliceMode { SLICE_WRITE = 0, SLICE_ACC_FIRST = 1, SLICE_ACC_NEXT = 2 };
+struct CompatDev {
+  int kind;          // dcrf_compat_kind; MATRIX is handled outside the slice/update kernels
+  float neg_w;       // Potts: -w
+  const float* diag; // Diagonal: Lp floats on the device (pads 0)
+};
+// standalone slice: m = alpha-weighted gather of val rows, optional post-norm, optional Potts/Diagonal;
+//   SLICE_WRITE      out  = m
+//   SLICE_ACC_FIRST  out  = (neg_unary ? -U : 0-U) - m       (U may be null -> treated as 0)
+//   SLICE_ACC_NEXT   out  = out - m
+void launch_slice(Ctx cx, const Lattice& lt, RowLayout rl, const float* val, const float* post_norm,
+                  const CompatDev* compat, int mode, const float* U, bool neg_unary, float* out);
+
+static const int kMaxFusedTerms = 8;
+struct FusedTerm {
+  const float* val;
+  const PixEntry* pix;
+  const float* post_norm;
+  const float* diag;
+  float neg_w;
+  float alpha;
+  int dp1;
+  int ckind;
+};
+struct FusedArgs {
+  int N, nterms;
+  const float* U;  // may be null (no unary)
+  int neg_unary;   // 1: start from -U (inference), 0: start from 0-U (stepInference)
+  float* Q;
+  FusedTerm t[kMaxFusedTerms];
+};
+bool fused_update_supported(RowLayout rl);
+// Q = softmax_col( -U - sum_k compat_k(norm_k * slice_k) ), everything in one pass
+void launch_fused_update(Ctx cx, RowLayout rl, const FusedArgs& a);
+// Q = softmax_col(acc) for any L (staged path)
+void launch_softmax(Ctx cx, RowLayout rl, int N, const float* acc, float* Q);
+// acc = -U / 0-U / -0 (no terms at all)
+void launch_init_acc(Ctx cx, RowLayout rl, int N, const float* U, bool neg_unary, float* acc);
+// out(mode) <- W * msg per pixel, W row-major LxL on the device; Eigen's GEBP summation order
+void launch_matrix_compat(Ctx cx, RowLayout rl, int N, const float* W, const float* msg, int mode, const float* U,
+                          bool neg_unary, float* out);
+
+// layout conversion at the boundary
+void launch_planes_to_rows(Ctx cx, RowLayout rl, int N, const float* planes_LxN, float* rows_NxLp);
+void launch_unpack_rows(Ctx cx, RowLayout rl, int N, const float* packed_NxL, float* rows_NxLp);
+void launch_pack_rows(Ctx cx, RowLayout rl, int N, const float* rows_NxLp, float* packed_NxL);
+void launch_fill(Ctx cx, float* p, size_t n, float v);
+// norm_raw -> 1/sqrt(x+1e-20) (symmetric) or 1/(x+1e-20), evaluated in double (pairwise.cpp:52-61)
+void launch_norm_transform(Ctx cx, int N, float* norm, bool symmetric);
+// U = Lmat * f for the logistic unary (unary.cpp:50-52); rows_NxLp out
+void launch_logistic_unary(Ctx cx, RowLayout rl, int N, int F, const float* Lmat_LxF, const float* f_FxN, float* U);
+// sums[0] += sum Q log max(Q,1e-20), sums[1] += sum U*Q, sums[2] += sum Q*T   (double accumulators on the device)
+void launch_kl_terms(Ctx cx, RowLayout rl, int N, const float* Q, const float* U, const float* T, double* sums);
+void launch_argmax(Ctx cx, RowLayout rl, int N, const float* Q, int16_t* labels);
+
+}  // namespace dcrf

@@ -1,0 +1,366 @@
+"""Parity of the CUDA path (through the public Python surface -> C-ABI) with the CPU oracle and the
+committed reference vectors.  Run on the B200 box: python -m pytest tests -m gpu.
+
+Tolerances (stated here, as BASELINE.json's north_star asks):
+  * lattice tables (vertex ids in first-touch order, barycentric weights, neighbour ids, keys): EXACT
+  * Permutohedral::compute (splat/blur/slice): EXACT (same float operations in the same order)
+  * Q after mean-field iterations: north_star allows max-abs 1e-4; the engine restates Eigen's
+    packet exp and summation order, so the tests hold it to Q_ATOL = 2e-6 (observed: 0 to a few ulp,
+    from the libm-expf tail lanes and, for MatrixCompatibility, nothing else)
+  * MAP: identical wherever the oracle's top-2 margin exceeds 1e-3
+  * KL divergence: relative 2e-5 (the reference accumulates the pairwise term in float; the engine in double)
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+Q_ATOL = 2e-6
+KL_RTOL = 2e-5
+
+
+@pytest.fixture(scope="module")
+def dcrf():
+    import pydensecrf_b200.densecrf as m
+
+    assert m.device_count() >= 1, "GPU tests need a CUDA device: there is no CPU fallback to fall back to"
+    return m
+
+
+@pytest.fixture(scope="module")
+def po(oracle_built):
+    return oracle_built
+
+
+def _golden(name):
+    return np.load(os.path.join(G, name))
+
+
+def _check_map(Q, Qref, margin=1e-3):
+    s = np.sort(Qref, axis=0)
+    sure = (s[-1] - s[-2]) > margin if Qref.shape[0] > 1 else np.ones(Qref.shape[1], bool)
+    assert np.array_equal(np.argmax(Q, 0)[sure], np.argmax(Qref, 0)[sure])
+
+
+def _lattice_of(dcrf, feats, L=1):
+    d = dcrf.DenseCRF(feats.shape[1], L)
+    d.addPairwiseEnergy(np.ascontiguousarray(feats, np.float32), 1.0)
+    return d
+
+
+# ---- lattice ---------------------------------------------------------------------------------------
+def test_lattice_golden_exact(dcrf):
+    g = _golden("lattice_small.npz")
+    for ci, (d, N) in enumerate(g["cases"]):
+        m = _lattice_of(dcrf, g["f%d" % ci])
+        off, bary, keys, nbr, _ = m._lattice_dump(0)
+        assert np.array_equal(off, g["ref_off%d" % ci]), (d, N)
+        assert np.array_equal(bary, g["ref_bary%d" % ci]), (d, N)
+        assert np.array_equal(nbr, g["ref_nbr%d" % ci]), (d, N)
+        for L in (1, 2, 3, 21):
+            y = m._lattice_filter(0, g["x%d_L%d" % (ci, L)])
+            assert np.array_equal(y, g["ref_y%d_L%d" % (ci, L)]), (d, N, L)
+
+
+@pytest.mark.parametrize("d,N,scale", [(2, 5000, 3.0), (5, 20001, 2.0), (5, 4096, 0.3), (3, 2, 1.0), (4, 777, 5.0),
+                                       (7, 3000, 1.5), (1, 640, 4.0), (9, 500, 1.0), (5, 1, 1.0)])
+def test_lattice_random_exact(dcrf, po, d, N, scale):
+    rng = np.random.default_rng(100 * d + N)
+    f = (rng.standard_normal((d, N)) * scale).astype(np.float32)
+    o = po.Lattice(f, "orc")
+    m = _lattice_of(dcrf, f)
+    assert m._lattice_info(0) == (d, N, o.V)
+    off, bary, keys, nbr, _ = m._lattice_dump(0)
+    ooff, obary, _, onbr = o.dump()
+    assert np.array_equal(keys, o.keys())      # the key SET and its first-touch numbering
+    assert np.array_equal(off, ooff)
+    assert np.array_equal(bary, obary)
+    assert np.array_equal(nbr, onbr)
+    for L in (1, 2, 4, 21, 37):
+        x = rng.standard_normal((N, L)).astype(np.float32)
+        assert np.array_equal(m._lattice_filter(0, x), o.filter(x)), L
+
+
+def test_lattice_ties_phantoms_and_duplicates(dcrf, po):
+    rng = np.random.default_rng(1)
+    # exact lattice positions: rank ties + round-half-even; N % 4 != 0: phantom origin simplex
+    f = rng.integers(-6, 7, (3, 1023)).astype(np.float32) * 0.5
+    # all pixels identical: one simplex, maximal contention on d+1 vertices
+    g = np.full((5, 4099), 1.2345, np.float32)
+    for feats in (f, g):
+        o = po.Lattice(feats, "orc")
+        m = _lattice_of(dcrf, feats)
+        off, bary, keys, nbr, _ = m._lattice_dump(0)
+        ooff, obary, _, onbr = o.dump()
+        assert m._lattice_info(0)[2] == o.V
+        assert np.array_equal(off, ooff) and np.array_equal(bary, obary) and np.array_equal(nbr, onbr)
+        x = rng.random((feats.shape[1], 3)).astype(np.float32)
+        assert np.array_equal(m._lattice_filter(0, x), o.filter(x))
+
+
+def test_lattice_2d_builders_exact(dcrf, po):
+    from tests import workloads as wl
+
+    W, H = 127, 65   # N % 4 != 0
+    img = wl.smooth_image(H, W, seed=2, grid=16)
+    d = dcrf.DenseCRF2D(W, H, 3)
+    d.addPairwiseGaussian(sxy=(3, 2), compat=1.0)
+    d.addPairwiseBilateral(sxy=(40, 30), srgb=(13, 11, 7), rgbim=img, compat=1.0)
+    o = po.CRF((W, H), 3, "orc")
+    o.addPairwiseGaussian((3, 2), 1.0)
+    o.addPairwiseBilateral((40, 30), (13, 11, 7), img, 1.0)
+    import ctypes as C
+    for k in range(2):
+        off, bary, keys, nbr, norm = d._lattice_dump(k)
+        lat = po.Lattice.__new__(po.Lattice)
+        lat.lib = po.load("orc")
+        lat.h = None
+        h = lat.lib.dll.orc_crf_term_lattice
+        h.restype = C.c_void_p
+        h.argtypes = [C.c_void_p, C.c_int]
+        lat.N, lat.d = W * H, (2, 5)[k]
+        hh = h(o.h, k)
+        lat.V = lat.lib.lattice_nvert(hh)
+        lat.h = hh
+        ooff, obary, _, onbr = lat.dump()
+        lat.h = None  # owned by the model
+        assert np.array_equal(off, ooff) and np.array_equal(bary, obary) and np.array_equal(nbr, onbr)
+        onorm = np.empty(W * H, np.float32)
+        lat.lib.crf_term_norm(o.h, k, onorm.ctypes.data_as(C.POINTER(C.c_float)))
+        assert np.array_equal(norm, onorm)
+
+
+# ---- mean-field ------------------------------------------------------------------------------------
+def test_toy_golden(dcrf):
+    g = _golden("toy.npz")
+    for nt in range(4):
+        d = dcrf.DenseCRF2D(10, 10, 2)
+        d.setUnaryEnergy(g["U"])
+        d.addPairwiseBilateral(sxy=2, srgb=2, rgbim=g["img"], compat=3, normalization=nt)
+        Q = np.array(d.inference(10))
+        assert np.abs(Q - g["ref_Q_nt%d" % nt]).max() <= Q_ATOL, nt
+    d = dcrf.DenseCRF(100, 2)
+    d.setUnaryEnergy(g["U"])
+    d.addPairwiseEnergy(g["generic_feats"], compat=3)
+    Q = np.array(d.inference(10))
+    assert np.abs(Q - g["ref_Q_generic"]).max() <= Q_ATOL
+    exp = np.zeros((10, 10), np.int64)
+    exp[2:8, 2:8] = 1
+    assert np.array_equal(np.argmax(Q, 0).reshape(10, 10), exp)
+
+
+@pytest.mark.parametrize("cname", ["potts", "diag", "matrix"])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_model_small_golden(dcrf, cname, mode):
+    g = _golden("model_small.npz")
+    cg, cb = {"potts": (3.0, 10.0), "diag": (g["Dg"], 4.0), "matrix": (g["Mx"], g["Mx"])}[cname]
+    worst = 0.0
+    for nt in range(4):
+        d = dcrf.DenseCRF2D(40, 30, 21)
+        d._set_iteration_mode(mode)   # 0: automatic (fused where possible), 1: staged kernels
+        d.setUnaryEnergy(g["U"])
+        d.addPairwiseGaussian(3, cg, normalization=nt)
+        d.addPairwiseBilateral(20, 13, g["img"], cb, normalization=nt)
+        ref = g["ref_Q_%s_nt%d" % (cname, nt)]
+        Q = np.array(d.inference(5))
+        worst = max(worst, np.abs(Q - ref).max())
+        assert np.abs(Q - ref).max() <= Q_ATOL, (nt, np.abs(Q - ref).max())
+        _check_map(Q, ref)
+        Q, t1, t2 = d.startInference()
+        kls = []
+        for _ in range(3):
+            kls.append(d.klDivergence(Q))
+            d.stepInference(Q, t1, t2)
+        np.testing.assert_allclose(kls, g["ref_KL_%s_nt%d" % (cname, nt)], rtol=KL_RTOL)
+    print("worst |dQ|", cname, mode, worst)
+
+
+def test_no_unary_golden(dcrf):
+    g = _golden("model_small.npz")
+    d = dcrf.DenseCRF2D(40, 30, 21)
+    d.addPairwiseGaussian(3, 3.0)
+    assert np.abs(np.array(d.inference(2)) - g["ref_Q_nounary"]).max() <= Q_ATOL
+    Q0 = np.array(d.startInference()[0])
+    assert Q0.shape == (21, 1200) and not Q0.any()
+
+
+def test_cfg1_im1_golden(dcrf):
+    """BASELINE configs[0]: examples/inference.py on im1.png + anno1.png, 5 iterations, both branches."""
+    g = _golden("cfg1_im1.npz")
+    img, U, L = g["img"], g["U"], int(g["n_labels"])
+    H, W = img.shape[:2]
+    d = dcrf.DenseCRF2D(W, H, L)
+    d.setUnaryEnergy(U)
+    d.addPairwiseGaussian(sxy=(3, 3), compat=3, kernel=dcrf.DIAG_KERNEL, normalization=dcrf.NORMALIZE_SYMMETRIC)
+    d.addPairwiseBilateral(sxy=(80, 80), srgb=(13, 13, 13), rgbim=img, compat=10, kernel=dcrf.DIAG_KERNEL,
+                           normalization=dcrf.NORMALIZE_SYMMETRIC)
+    Q = np.array(d.inference(5))
+    assert np.abs(Q - g["ref_Q_2d"]).max() <= Q_ATOL
+    assert np.array_equal(np.argmax(Q, 0), np.argmax(g["ref_Q_2d"], 0))
+    Q, t1, t2 = d.startInference()
+    kls = []
+    for _ in range(5):
+        kls.append(d.klDivergence(Q))
+        d.stepInference(Q, t1, t2)
+    np.testing.assert_allclose(kls, g["ref_KL_2d"], rtol=KL_RTOL)
+
+    from pydensecrf_b200.utils import create_pairwise_bilateral, create_pairwise_gaussian
+
+    d = dcrf.DenseCRF(W * H, L)
+    d.setUnaryEnergy(U)
+    d.addPairwiseEnergy(create_pairwise_gaussian(sdims=(3, 3), shape=img.shape[:2]), compat=3)
+    d.addPairwiseEnergy(create_pairwise_bilateral(sdims=(80, 80), schan=(13, 13, 13), img=img, chdim=2), compat=10)
+    Q = np.array(d.inference(5))
+    assert np.abs(Q - g["ref_Q_generic"]).max() <= Q_ATOL
+
+
+def test_mid_golden(dcrf):
+    from tests import workloads as wl
+
+    g = _golden("mid_160x120.npz")
+    W, H, L = 160, 120, 21
+    d = dcrf.DenseCRF2D(W, H, L)
+    d.setUnaryEnergy(wl.softmax_unary(H, W, L, seed=5, grid=8))
+    d.addPairwiseGaussian(3, 3.0)
+    d.addPairwiseBilateral(80, 13, wl.smooth_image(H, W, seed=5, grid=16), 10.0)
+    Qm = d.inference(10)
+    Q = np.array(Qm)
+    assert np.abs(Q[:, ::5] - g["ref_Q_sub"]).max() <= Q_ATOL
+    sure = g["ref_margin"] > 1e-3
+    assert np.array_equal(np.argmax(Q, 0)[sure], g["ref_MAP"][sure])
+    assert np.array_equal(d.currentMap(Qm)[sure], g["ref_MAP"][sure])
+
+
+@pytest.mark.parametrize("L,W,H", [(2, 64, 48), (3, 50, 34), (7, 61, 47), (21, 128, 96), (150, 40, 30), (33, 31, 29)])
+def test_inference_vs_oracle(dcrf, po, L, W, H):
+    from tests import workloads as wl
+
+    rng = np.random.default_rng(L)
+    img = wl.smooth_image(H, W, seed=L, grid=8)
+    U = wl.softmax_unary(H, W, L, seed=L, grid=8)
+    Mx = wl.matrix_compat(L, seed=L)
+    Dg = (-rng.random(L) * 3).astype(np.float32)
+    for cg, cb in [(3.0, 10.0), (Dg, Mx), (Mx, 5.0)]:
+        d = dcrf.DenseCRF2D(W, H, L)
+        o = po.CRF((W, H), L, "orc")
+        for c in (d, o):
+            c.setUnaryEnergy(U)
+            c.addPairwiseGaussian((3, 2), cg)
+            c.addPairwiseBilateral((30, 25), (13, 11, 9), img, cb)
+        Q, Qo = np.array(d.inference(4)), o.inference(4)
+        err = np.abs(Q - Qo).max()
+        assert err <= Q_ATOL, (L, err)
+        _check_map(Q, Qo)
+        np.testing.assert_allclose(d.klDivergence(d.inference(2)), o.klDivergence(np.array(o.inference(2))), rtol=KL_RTOL)
+
+
+def test_logistic_unary(dcrf, po):
+    rng = np.random.default_rng(9)
+    N, L, F = 300, 4, 6
+    f = rng.standard_normal((3, N)).astype(np.float32)
+    Lm = rng.standard_normal((L, F)).astype(np.float32)
+    ff = rng.standard_normal((F, N)).astype(np.float32)
+    d = dcrf.DenseCRF(N, L)
+    d.setUnary(dcrf.LogisticUnary(Lm, ff))
+    d.addPairwiseEnergy(f, 2.0)
+    o = po.CRF(N, L, "orc")
+    o.setUnaryLogistic(Lm, ff)
+    o.addPairwiseEnergy(f, 2.0)
+    assert np.abs(np.array(d.inference(3)) - o.inference(3)).max() <= 1e-5
+
+
+def test_step_equals_inference_and_views(dcrf):
+    from tests import workloads as wl
+
+    W, H, L = 64, 48, 5
+    d = dcrf.DenseCRF2D(W, H, L)
+    d.setUnaryEnergy(wl.softmax_unary(H, W, L, seed=2, grid=8))
+    d.addPairwiseGaussian(3, 3.0)
+    d.addPairwiseBilateral(30, 13, wl.smooth_image(H, W, seed=2, grid=8), 10.0)
+    Qi = np.array(d.inference(4))
+    Q, t1, t2 = d.startInference()
+    for _ in range(4):
+        d.stepInference(Q, t1, t2)
+    assert np.array_equal(np.array(Q), Qi)   # stepwise == inference(n), bit for bit
+    # a live zero-copy view observes the next step, and writes through it are used by the next step
+    Q, t1, t2 = d.startInference()
+    view = np.asarray(Q)
+    assert view.shape == (L, W * H) and view.strides == (4, 4 * L) and view.flags.writeable
+    before = view.copy()
+    d.stepInference(Q, t1, t2)
+    assert not np.array_equal(view, before)
+    view[...] = before          # write the old Q back through the view
+    d.stepInference(Q, t1, t2)  # must redo exactly the first step
+    Q2, a, b = d.startInference()
+    d.stepInference(Q2, a, b)
+    assert np.array_equal(np.asarray(Q), np.array(Q2))
+
+
+def test_fused_equals_staged_and_deterministic(dcrf):
+    from tests import workloads as wl
+
+    W, H, L = 320, 240, 21
+    U = wl.softmax_unary(H, W, L, seed=4)
+    img = wl.smooth_image(H, W, seed=4)
+    res = []
+    for mode in (2, 1, 2):
+        d = dcrf.DenseCRF2D(W, H, L)
+        d._set_iteration_mode(mode)
+        d.setUnaryEnergy(U)
+        d.addPairwiseGaussian(3, 3.0)
+        d.addPairwiseBilateral(80, 13, img, 10.0)
+        res.append(np.array(d.inference(10)))
+    assert np.array_equal(res[0], res[1])   # fused kernel == staged kernels, bit for bit
+    assert np.array_equal(res[0], res[2])   # run-to-run deterministic (no float atomics anywhere)
+    assert np.allclose(res[0].sum(0), 1.0, atol=1e-5)
+
+
+def test_512_vs_oracle(dcrf, po):
+    """cfg 4 unit (one 512x512, 21 labels, 5 iterations) against the oracle."""
+    from tests import workloads as wl
+
+    W = H = 512
+    L = 21
+    U = wl.softmax_unary(H, W, L, seed=8)
+    img = wl.smooth_image(H, W, seed=8)
+    d = dcrf.DenseCRF2D(W, H, L)
+    o = po.CRF((W, H), L, "orc")
+    for c in (d, o):
+        c.setUnaryEnergy(U)
+        c.addPairwiseGaussian(3, 3.0)
+        c.addPairwiseBilateral(80, 13, img, 10.0)
+    Q, Qo = np.array(d.inference(5)), o.inference(5)
+    assert np.abs(Q - Qo).max() <= Q_ATOL
+    _check_map(Q, Qo)
+
+
+def test_1080p_properties(dcrf):
+    """BASELINE configs[1] at full size: size-independent properties (the oracle takes ~20 s here, so the
+    value check at this size lives in bench.py's cpu_baseline leg, which compares Q on the same input)."""
+    from tests import workloads as wl
+
+    W, H, L = 1920, 1080, 21
+    U = wl.softmax_unary(H, W, L, seed=0)
+    img = wl.smooth_image(H, W, seed=0)
+    d = dcrf.DenseCRF2D(W, H, L)
+    d.setUnaryEnergy(U)
+    d.addPairwiseGaussian(3, 3.0)
+    d.addPairwiseBilateral(80, 13, img, 10.0)
+    Qm = d.inference(10)
+    Q = np.array(Qm)
+    assert Q.shape == (L, W * H) and np.isfinite(Q).all() and (Q >= 0).all()
+    assert np.abs(Q.sum(0) - 1.0).max() <= 1e-5
+    assert np.array_equal(d.currentMap(Qm), np.argmax(Q, 0).astype(np.int16))
+    assert np.array_equal(np.array(d.inference(10)), Q)            # deterministic
+    Qs, a, b = d.startInference()
+    kl = []
+    for _ in range(4):
+        kl.append(d.klDivergence(Qs))
+        d.stepInference(Qs, a, b)
+    assert all(x > y for x, y in zip(kl, kl[1:]))                    # mean-field lowers the KL divergence
+    for k, (dd, frac_lo, frac_hi) in enumerate([(2, 0.05, 0.3), (5, 0.05, 1.5)]):
+        d_, N_, V_ = d._lattice_info(k)
+        assert d_ == dd and N_ == W * H and frac_lo * N_ < V_ < frac_hi * N_
