@@ -8,7 +8,8 @@ Tolerances (stated here, as BASELINE.json's north_star asks):
     packet exp and summation order, so the tests hold it to Q_ATOL = 2e-6 (observed: 0 to a few ulp,
     from the libm-expf tail lanes and, for MatrixCompatibility, nothing else)
   * MAP: identical wherever the oracle's top-2 margin exceeds 1e-3
-  * KL divergence: relative 2e-5 (the reference accumulates the pairwise term in float; the engine in double)
+  * KL divergence: relative 2e-4 (the reference sums each pairwise term as ONE float over all L*N products,
+    densecrf.cpp:232, which alone carries ~1e-4 relative error at these sizes; the engine accumulates in double)
 """
 import os
 
@@ -19,7 +20,7 @@ pytestmark = pytest.mark.gpu
 
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 Q_ATOL = 2e-6
-KL_RTOL = 2e-5
+KL_RTOL = 2e-4
 
 
 @pytest.fixture(scope="module")
