@@ -178,6 +178,16 @@ def run_b200(args):
     ms_per_step = ms_max / args.steps
     value = world * N * N_ITER / (ms_per_step * 1e-3) / 1e6
 
+    # ---- secondary: same timed loop with the approximate ("fast") softmax; the headline stays bit-faithful ----
+    d.setSoftmaxMode(True)
+    for _ in range(3):
+        d.inferenceInto(N_ITER, Q)
+    d._timer_start()
+    for _ in range(args.steps):
+        d.inferenceInto(N_ITER, Q)
+    ms_fast = max_over_ranks(d._timer_stop(), dist, torch, local) / args.steps
+    d.setSoftmaxMode(False)
+
     # ---- end to end through the public API: host unary in, host Q out, every step --------------------
     for _ in range(2):
         d.setUnaryEnergy(U)
@@ -228,7 +238,10 @@ def run_b200(args):
                       "l2": "per-step working set ~0.9 GB (U, Q, lattice tables, value buffers) > 126 MB L2: no flush needed",
                       "init_ms": {"set_unary": (t1 - t0) * 1e3, "gaussian_lattice": (t2 - t1) * 1e3,
                                   "bilateral_lattice": (t3 - t2) * 1e3}},
-           "ms_per_inference": ms_per_step, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+           "ms_per_inference": ms_per_step,
+           "fast_softmax": {"ms_per_step": ms_fast, "value": world * N * N_ITER / (ms_fast * 1e-3) / 1e6,
+                            "note": "setSoftmaxMode(True): ex2-based exp, tree sum, reciprocal; not the default"},
+           "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
            "roofline": roofline}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -159,6 +159,10 @@ dcrf_status dcrf_pairwise_apply(dcrf_t* m, int k, dcrf_mat_t* Q, dcrf_mat_t** ou
 /* 0 = pick automatically, 1 = force the staged (unfused) iteration, 2 = force the fused iteration (fails if
  * the model has a term the fused kernel cannot take) */
 dcrf_status dcrf_set_iteration_mode(dcrf_t* m, int mode);
+/* 0 (default) = bit-faithful softmax: Eigen's packet exp polynomial, Eigen's summation order, IEEE division,
+ * so Q equals the reference's to the last bit except for rare last-ulp differences in the L%4 tail labels;
+ * 1 = fast softmax in the fused kernel: ex2-based exp, tree sum, reciprocal multiply (~1e-6 relative). */
+dcrf_status dcrf_set_softmax_mode(dcrf_t* m, int fast);
 
 #ifdef __cplusplus
 }

@@ -62,6 +62,7 @@ cdef extern from "dcrf_b200.h" nogil:
     int dcrf_lattice_filter(dcrf_t* m, int k, const float* inp, int L, float* out)
     int dcrf_pairwise_apply(dcrf_t* m, int k, dcrf_mat_t* Q, dcrf_mat_t** out)
     int dcrf_set_iteration_mode(dcrf_t* m, int mode)
+    int dcrf_set_softmax_mode(dcrf_t* m, int fast)
 
 
 class KernelType(enum.IntEnum):
@@ -468,6 +469,10 @@ cdef class DenseCRF:
 
     def _set_iteration_mode(self, int mode):
         _check(dcrf_set_iteration_mode(self._h, mode))
+
+    def setSoftmaxMode(self, bint fast):
+        """False (default): bit-faithful softmax; True: faster approximate softmax (~1e-6 relative)."""
+        _check(dcrf_set_softmax_mode(self._h, 1 if fast else 0))
 
     def _num_pairwise(self):
         return dcrf_num_pairwise(self._h)

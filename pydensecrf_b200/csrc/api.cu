@@ -174,9 +174,15 @@ struct dcrf_model {
   float* msg = nullptr;  // staged path / KL: one message
   double* kl_sums = nullptr;
   int iter_mode = 0;
+  bool fast_softmax = false;
   cudaEvent_t t0 = nullptr, t1 = nullptr;
   char* flush_buf = nullptr;
   size_t flush_bytes = 0;
+  // side streams: the filters of terms 1.. run beside term 0 (they only meet in the update kernel)
+  std::vector<cudaStream_t> aux;
+  std::vector<cudaEvent_t> aux_done;
+  cudaEvent_t fork = nullptr;
+  bool overlap_terms = true;
   Ctx cx() { return Ctx{stream, &prof}; }
 };
 
@@ -268,6 +274,7 @@ const float* run_filter(Ctx cx, const Lattice& lt, RowLayout rl, const float* in
 
 bool can_fuse(dcrf_model* m) {
   if (!fused_update_supported(m->rl) || (int)m->terms.size() > kMaxFusedTerms) return false;
+  if ((uint64_t)m->N * m->rl.Lp >= (1ull << 31)) return false;  // the fused kernel indexes rows with 32 bits
   for (Term* t : m->terms)
     if (t->ckind == DCRF_COMPAT_MATRIX) return false;
   return true;
@@ -309,11 +316,34 @@ void mf_step(dcrf_model* m, float* Q, bool neg_unary) {
     a.U = m->U;
     a.neg_unary = neg_unary ? 1 : 0;
     a.Q = Q;
+    for (int k = 0; k < a.nterms; k++) ensure_val(m, m->terms[k]);
+    // per-launch profiling wants clean, serialised durations: no overlap while it is on
+    const bool overlap = m->overlap_terms && a.nterms > 1 && !m->prof.enabled;
+    if (overlap) {
+      while ((int)m->aux.size() < a.nterms - 1) {
+        cudaStream_t s2;
+        cudaEvent_t e2;
+        DCRF_CUDA(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+        DCRF_CUDA(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+        m->aux.push_back(s2);
+        m->aux_done.push_back(e2);
+      }
+      if (!m->fork) DCRF_CUDA(cudaEventCreateWithFlags(&m->fork, cudaEventDisableTiming));
+      DCRF_CUDA(cudaEventRecord(m->fork, m->stream));
+    }
     for (int k = 0; k < a.nterms; k++) {
       Term* t = m->terms[k];
-      ensure_val(m, t);
       FusedTerm& ft = a.t[k];
-      ft.val = run_filter(cx, t->lat, m->rl, Q, t->pre() ? t->norm : nullptr, t->valA, t->valB);
+      Ctx ck = cx;
+      if (overlap && k > 0) {
+        ck.stream = m->aux[k - 1];
+        DCRF_CUDA(cudaStreamWaitEvent(ck.stream, m->fork, 0));
+      }
+      ft.val = run_filter(ck, t->lat, m->rl, Q, t->pre() ? t->norm : nullptr, t->valA, t->valB);
+      if (overlap && k > 0) {
+        DCRF_CUDA(cudaEventRecord(m->aux_done[k - 1], ck.stream));
+        DCRF_CUDA(cudaStreamWaitEvent(m->stream, m->aux_done[k - 1], 0));
+      }
       ft.pix = t->lat.pix;
       ft.post_norm = t->post() ? t->norm : nullptr;
       ft.diag = t->diag;
@@ -322,7 +352,7 @@ void mf_step(dcrf_model* m, float* Q, bool neg_unary) {
       ft.dp1 = t->lat.d + 1;
       ft.ckind = t->ckind;
     }
-    launch_fused_update(cx, m->rl, a);
+    launch_fused_update(cx, m->rl, a, m->fast_softmax);
   } else {
     ensure_scratch(m);
     if (m->terms.empty()) launch_init_acc(cx, m->rl, m->N, m->U, neg_unary, m->acc);
@@ -335,10 +365,10 @@ void mf_step(dcrf_model* m, float* Q, bool neg_unary) {
 // Q0 = expAndNormalize(-unary) (densecrf.cpp:120)
 void mf_init(dcrf_model* m, float* Q) {
   Ctx cx = m->cx();
-  if (m->iter_mode != 1 && fused_update_supported(m->rl)) {
+  if (m->iter_mode != 1 && fused_update_supported(m->rl) && (uint64_t)m->N * m->rl.Lp < (1ull << 31)) {
     FusedArgs a;
     a.N = m->N, a.nterms = 0, a.U = m->U, a.neg_unary = 1, a.Q = Q;
-    launch_fused_update(cx, m->rl, a);
+    launch_fused_update(cx, m->rl, a, m->fast_softmax);
   } else {
     ensure_scratch(m);
     launch_init_acc(cx, m->rl, m->N, m->U, true, m->acc);
@@ -530,6 +560,9 @@ void dcrf_destroy(dcrf_t* m) {
     for (Term* t : m->terms) term_free(m, t);
     for (void* p : {(void*)m->U, (void*)m->acc, (void*)m->msg, (void*)m->kl_sums, (void*)m->flush_buf}) dev_free(p, m->stream);
     cudaStreamSynchronize(m->stream);
+    for (cudaStream_t s2 : m->aux) cudaStreamDestroy(s2);
+    for (cudaEvent_t e2 : m->aux_done) cudaEventDestroy(e2);
+    if (m->fork) cudaEventDestroy(m->fork);
     m->prof.destroy();
     cudaEventDestroy(m->t0);
     cudaEventDestroy(m->t1);
@@ -947,6 +980,12 @@ dcrf_status dcrf_set_iteration_mode(dcrf_t* m, int mode) {
   return guarded([&] {
     DCRF_REQUIRE(m && mode >= 0 && mode <= 2, "bad iteration mode");
     m->iter_mode = mode;
+  });
+}
+dcrf_status dcrf_set_softmax_mode(dcrf_t* m, int fast) {
+  return guarded([&] {
+    DCRF_REQUIRE(m, "null argument");
+    m->fast_softmax = fast != 0;
   });
 }
 

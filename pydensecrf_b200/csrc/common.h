@@ -138,6 +138,7 @@ struct Lattice {
   int* csr_start = nullptr;    // [V+1]
   CsrEntry* csr = nullptr;     // [E]
   int2* nbr = nullptr;         // [(d+1)*V] rows (id+1) of the -/+ neighbours, 0 = absent
+  int* order = nullptr;        // [V] splat work order: windows of 4096 vertex ids, inside a window by CSR row length
   int16_t* keys = nullptr;     // [V*d]
   float alpha = 1.f;           // 1/(1+2^-d)
   int max_row = 0;             // longest CSR row (diagnostic)
@@ -188,7 +189,7 @@ struct FusedArgs {
 };
 bool fused_update_supported(RowLayout rl);
 // Q = softmax_col( -U - sum_k compat_k(norm_k * slice_k) ), everything in one pass
-void launch_fused_update(Ctx cx, RowLayout rl, const FusedArgs& a);
+void launch_fused_update(Ctx cx, RowLayout rl, const FusedArgs& a, bool fast);
 // Q = softmax_col(acc) for any L (staged path)
 void launch_softmax(Ctx cx, RowLayout rl, int N, const float* acc, float* Q);
 // acc = -U / 0-U / -0 (no terms at all)

@@ -302,6 +302,15 @@ __global__ void k_fill_csr(uint32_t E, int dp1, const uint32_t* __restrict__ sor
   csr[e] = c;
 }
 
+// splat work order: keep the coarse first-touch (scan-line) order for cache locality but, inside a window of
+// 4096 vertices, line vertices up by CSR row length so the lanes of a warp loop about equally often
+__global__ void k_order_keys(int V, const int* __restrict__ count, uint32_t* __restrict__ key, uint32_t* __restrict__ val) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  key[v] = ((uint32_t)(v >> 12) << 8) | (uint32_t)min(count[v], 255);
+  val[v] = (uint32_t)v;
+}
+
 __global__ void k_max_int(int n, const int* __restrict__ a, int* __restrict__ out) {
   int m = 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = max(m, a[i]);
@@ -441,6 +450,21 @@ void build_impl(Ctx cx, const ElevateParams& ep, Lattice* L) {
       k_fill_csr<<<blocks_for(E), kThreads, 0, s>>>(E, dp1, sval2, bary, L->csr);
     }
   }
+  L->order = dev_alloc<int>((size_t)V, s);
+  if (V > 0) {
+    LaunchScope ls(cx.prof, s, "lattice_order");
+    uint32_t* okey = dev_alloc<uint32_t>(V, s);
+    uint32_t* okey2 = dev_alloc<uint32_t>(V, s);
+    uint32_t* oval = dev_alloc<uint32_t>(V, s);
+    k_order_keys<<<blocks_for(V), kThreads, 0, s>>>(V, count, okey, oval);
+    int bits = 9;
+    while ((1ull << (bits - 8)) <= ((uint64_t)V >> 12)) bits++;
+    size_t tmp_bytes = 0;
+    DCRF_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, okey, okey2, oval, (uint32_t*)L->order, V, 0, bits, s));
+    void* tmp = dev_alloc<char>(tmp_bytes, s);
+    DCRF_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, okey, okey2, oval, (uint32_t*)L->order, V, 0, bits, s));
+    for (void* q : {(void*)tmp, (void*)okey, (void*)okey2, (void*)oval}) dev_free(q, s);
+  }
   if (V > 0) {
     LaunchScope ls(cx.prof, s, "lattice_neighbours");
     dim3 grid(blocks_for(V), dp1);
@@ -466,6 +490,8 @@ void Lattice::release(cudaStream_t s) {
   dev_free(csr, s);
   dev_free(nbr, s);
   dev_free(keys, s);
+  dev_free(order, s);
+  order = nullptr;
   pix = nullptr;
   csr_start = nullptr;
   csr = nullptr;

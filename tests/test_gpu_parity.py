@@ -319,6 +319,28 @@ def test_fused_equals_staged_and_deterministic(dcrf):
     assert np.allclose(res[0].sum(0), 1.0, atol=1e-5)
 
 
+def test_fast_softmax_mode_within_tolerance(dcrf, po):
+    """setSoftmaxMode(True) trades the bit-faithful softmax for an ex2-based one; it must still meet
+    north_star's 1e-4 / MAP bar (held to 2e-5 here)."""
+    from tests import workloads as wl
+
+    W, H, L = 256, 192, 21
+    U = wl.softmax_unary(H, W, L, seed=6)
+    img = wl.smooth_image(H, W, seed=6)
+    d = dcrf.DenseCRF2D(W, H, L)
+    d.setSoftmaxMode(True)
+    o = po.CRF((W, H), L, "orc")
+    for c in (d, o):
+        c.setUnaryEnergy(U)
+        c.addPairwiseGaussian(3, 3.0)
+        c.addPairwiseBilateral(80, 13, img, 10.0)
+    Q, Qo = np.array(d.inference(10)), o.inference(10)
+    err = np.abs(Q - Qo).max()
+    print("fast softmax max|dQ| after 10 iterations:", err)
+    assert err <= 2e-5
+    _check_map(Q, Qo)
+
+
 def test_512_vs_oracle(dcrf, po):
     """cfg 4 unit (one 512x512, 21 labels, 5 iterations) against the oracle."""
     from tests import workloads as wl
