@@ -87,7 +87,14 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def dist_setup(n_gpus):
+_BACKEND = "nccl"
+
+
+def dist_setup(n_gpus, backend="nccl"):
+    """One process per GPU (torchrun sets RANK/LOCAL_RANK/WORLD_SIZE/MASTER_*).  The path has no exchange
+    step, so the process group only carries the barrier and the max-over-ranks of the elapsed time."""
+    global _BACKEND
+    _BACKEND = backend
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -95,16 +102,28 @@ def dist_setup(n_gpus):
         import torch
         import torch.distributed as dist
 
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend)
         return world, rank, local, dist, torch
     return 1, 0, 0, None, None
+
+
+def shard_of(rank, world, n_units):
+    """Units (images) a rank owns when a batch is split over replicas: contiguous blocks, remainder to the
+    first ranks.  bench's 1080p workload uses one image per rank (seed = rank); cfg 4 style batches use this."""
+    base, rem = divmod(n_units, world)
+    lo = rank * base + min(rank, rem)
+    return range(lo, lo + base + (1 if rank < rem else 0))
 
 
 def max_over_ranks(x, dist, torch, local):
     if dist is None:
         return x
-    t = torch.tensor([x], dtype=torch.float64, device=torch.device("cuda", local))
+    dev = torch.device("cuda", local) if _BACKEND == "nccl" else torch.device("cpu")
+    t = torch.tensor([x], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
 
@@ -112,7 +131,28 @@ def max_over_ranks(x, dist, torch, local):
 def barrier(dist, torch):
     if dist is not None:
         dist.barrier()
-        torch.cuda.synchronize()
+        if _BACKEND == "nccl":
+            torch.cuda.synchronize()
+
+
+def dist_selftest():
+    """CPU check of the multi-process plumbing (gloo): every rank 'times' 10*(rank+1) ms; the reported step
+    time must be the max over ranks and the aggregate must count every rank's units."""
+    world, rank, local, dist, torch = dist_setup(0, backend="gloo")
+    barrier(dist, torch)
+    ms = max_over_ranks(10.0 * (rank + 1), dist, torch, local)
+    units = list(shard_of(rank, world, 7))
+    total = max_over_ranks(float(len(units)), dist, torch, local)  # exercised twice on purpose
+    owned = [None] * world
+    if dist is not None:
+        dist.all_gather_object(owned, units)
+    else:
+        owned = [units]
+    barrier(dist, torch)
+    if rank == 0:
+        print(json.dumps({"world": world, "ms": ms, "max_units": total, "owned": owned}))
+    if dist is not None:
+        dist.destroy_process_group()
 
 
 def kernel_bytes(name, lat):
@@ -189,21 +229,35 @@ def run_b200(args):
     d.setSoftmaxMode(False)
 
     # ---- end to end through the public API: host unary in, host Q out, every step --------------------
-    for _ in range(2):
-        d.setUnaryEnergy(U)
-        np.asarray(d.inference(N_ITER))
-    barrier(dist, torch)
-    e0 = time.perf_counter()
-    for _ in range(args.steps):
-        d.setUnaryEnergy(U)                 # H2D of this step's input
-        Qh = np.asarray(d.inference(N_ITER))  # D2H of this step's result
-    d.synchronize()
-    e_ms = (time.perf_counter() - e0) * 1e3
-    barrier(dist, torch)
-    e_ms = max_over_ranks(e_ms, dist, torch, local) / args.steps
+    from pydensecrf_b200.utils import pinned_empty
+
+    Up = pinned_empty(U.shape, np.float32)   # the step's input sits in page-locked host memory
+    Up[...] = U
+
+    def e2e_loop(Uh, fetch):
+        for _ in range(2):
+            d.setUnaryEnergy(Uh)
+            fetch(d.inference(N_ITER))
+        barrier(dist, torch)
+        t_0 = time.perf_counter()
+        for _ in range(args.steps):
+            d.setUnaryEnergy(Uh)              # H2D of this step's input (L*N floats)
+            out_h = fetch(d.inference(N_ITER))  # D2H of this step's result
+        d.synchronize()
+        t_ms = (time.perf_counter() - t_0) * 1e3
+        barrier(dist, torch)
+        return max_over_ranks(t_ms, dist, torch, local) / args.steps, out_h
+
+    e_ms, Qh = e2e_loop(Up, np.asarray)
+    e_ms_pageable, _ = e2e_loop(U, np.asarray)
+    e_ms_map, Mh = e2e_loop(Up, d.currentMap)
     e2e = {"value": world * N * N_ITER / (e_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": e_ms,
            "h2d_bytes_per_step": int(U.nbytes), "d2h_bytes_per_step": int(Qh.nbytes),
-           "api": "setUnaryEnergy(U) + np.asarray(inference(10)) per step, pageable numpy buffers"}
+           "api": "setUnaryEnergy(U_pinned) + np.asarray(inference(10)) per step: full Q (L*N floats) back to the host",
+           "pageable_input_ms_per_step": e_ms_pageable,
+           "map_output": {"ms_per_step": e_ms_map, "value": world * N * N_ITER / (e_ms_map * 1e-3) / 1e6,
+                          "d2h_bytes_per_step": int(Mh.nbytes),
+                          "api": "same, but currentMap(Q): the int16 label map comes back instead of Q"}}
 
     # ---- per-kernel durations: same steps, every launch bracketed by CUDA events ---------------------
     d._profile_enable(True)
@@ -326,7 +380,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dist-selftest", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.dist_selftest:
+        return dist_selftest()
     if args.impl == "reference":
         run_reference(args)
     else:

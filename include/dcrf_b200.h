@@ -121,6 +121,13 @@ dcrf_status dcrf_mat_host_ptr(dcrf_mat_t* a, float** ptr);
 /* a buffer view ended (the .pyx's __releasebuffer__, pydensecrf/eigen.pyx:97): the host copy may have been written */
 void dcrf_mat_release_host(dcrf_mat_t* a);
 
+/* ---- page-locked host memory ------------------------------------------------------------------- */
+/* Host arrays passed to this library may live anywhere; arrays in page-locked memory are transferred by
+ * DMA at full PCIe rate (pageable ones are staged by the driver at a fraction of it).  These two hand out
+ * and take back page-locked blocks from the library's pool (pydensecrf_b200.utils.pinned_empty wraps them). */
+dcrf_status dcrf_host_alloc(size_t bytes, void** out);
+void dcrf_host_free(void* p, size_t bytes);
+
 /* ---- measurement (bench.py) ------------------------------------------------------------------- */
 dcrf_status dcrf_synchronize(dcrf_t* m);
 /* CUDA events on the model's own stream: start, then stop returns elapsed milliseconds */

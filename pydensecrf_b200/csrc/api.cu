@@ -99,6 +99,40 @@ struct PinnedPool {
 };
 static PinnedPool g_pinned;
 
+// device buffers of result matrices, recycled per (device, size): inference() returns a fresh matrix on
+// every call, and cudaMalloc/cudaFree of ~200 MB would otherwise sit on the end-to-end path
+struct DevicePool {
+  std::mutex mu;
+  std::multimap<std::pair<int, size_t>, void*> free_blocks;
+  size_t cached = 0;
+  static constexpr size_t kMaxCached = 16ull << 30;
+  void* get(int device, size_t bytes) {
+    {
+      std::lock_guard<std::mutex> g(mu);
+      auto it = free_blocks.find({device, bytes});
+      if (it != free_blocks.end()) {
+        void* p = it->second;
+        free_blocks.erase(it);
+        cached -= bytes;
+        return p;
+      }
+    }
+    void* p = nullptr;
+    DCRF_CUDA(cudaMalloc(&p, bytes ? bytes : 1));
+    return p;
+  }
+  void put(int device, void* p, size_t bytes) {
+    std::lock_guard<std::mutex> g(mu);
+    if (cached + bytes > kMaxCached) {
+      cudaFree(p);
+      return;
+    }
+    free_blocks.emplace(std::make_pair(device, bytes), p);
+    cached += bytes;
+  }
+};
+static DevicePool g_devpool;
+
 struct DeviceGuard {
   int prev = -1;
   explicit DeviceGuard(int dev) {
@@ -122,8 +156,9 @@ struct dcrf_mat {
   float* host = nullptr;  // rows*cols floats, col-major (pixel-major); malloc'd or pinned
   bool host_pinned = false;
   float* dev = nullptr;   // cols rows of RowLayout(rows).Lp floats
+  size_t dev_bytes = 0;
   int device = -1;
-  cudaEvent_t ready = nullptr;  // recorded after the last device write
+  cudaEvent_t ready = nullptr;  // recorded after the last device use (read or write)
   bool host_valid = false, dev_valid = false;
   int exports = 0;              // live buffer views
   size_t bytes() const { return (size_t)rows * cols * sizeof(float); }
@@ -140,7 +175,8 @@ static void mat_free_host(dcrf_mat* a) {
 static void mat_free_dev(dcrf_mat* a) {
   if (a->dev) {
     DeviceGuard g(a->device);
-    cudaFree(a->dev);
+    if (a->ready) cudaEventSynchronize(a->ready);  // nothing queued may still touch the buffer
+    g_devpool.put(a->device, a->dev, a->dev_bytes);
     a->dev = nullptr;
   }
   if (a->ready) {
@@ -397,7 +433,8 @@ float* mat_device(dcrf_model* m, dcrf_mat* a, bool need_contents) {
   }
   const size_t n = (size_t)m->N * m->rl.Lp;
   if (!a->dev) {
-    DCRF_CUDA(cudaMalloc(&a->dev, n * sizeof(float)));
+    a->dev_bytes = n * sizeof(float);
+    a->dev = (float*)g_devpool.get(m->device, a->dev_bytes);
     a->device = m->device;
     a->dev_valid = false;
   }
@@ -731,6 +768,7 @@ dcrf_status dcrf_kl_divergence(dcrf_t* m, dcrf_mat_t* Q, double* out) {
       term_apply(m, t, q, SLICE_WRITE, false, m->acc);
       launch_kl_terms(cx, m->rl, m->N, q, nullptr, m->acc, m->kl_sums);
     }
+    DCRF_CUDA(cudaEventRecord(Q->ready, m->stream));
     double h[3];
     DCRF_CUDA(cudaMemcpyAsync(h, m->kl_sums, sizeof(h), cudaMemcpyDeviceToHost, m->stream));
     DCRF_CUDA(cudaStreamSynchronize(m->stream));
@@ -817,6 +855,18 @@ void dcrf_mat_release_host(dcrf_mat_t* a) {
   // the view was writable (readonly=0 in the reference's buffer, eigen.pyx:40,92): assume it was written
   a->dev_valid = false;
   a->host_valid = true;
+}
+
+// ---- pinned host buffers for callers ---------------------------------------------------------------
+dcrf_status dcrf_host_alloc(size_t bytes, void** out) {
+  return guarded([&] {
+    DCRF_REQUIRE(out, "null argument");
+    pick_device(-1);  // pinned memory needs a CUDA context
+    *out = g_pinned.get(bytes);
+  });
+}
+void dcrf_host_free(void* p, size_t bytes) {
+  if (p) g_pinned.put(p, bytes);
 }
 
 // ---- measurement -----------------------------------------------------------------------------------
@@ -967,6 +1017,7 @@ dcrf_status dcrf_pairwise_apply(dcrf_t* m, int k, dcrf_mat_t* Q, dcrf_mat_t** ou
     float* o = mat_device(m, a, false);
     term_apply(m, m->terms[k], q, SLICE_WRITE, false, o);
     DCRF_CUDA(cudaGetLastError());
+    DCRF_CUDA(cudaEventRecord(Q->ready, m->stream));
     mat_written(m, a);
   });
   if (st != DCRF_OK) {

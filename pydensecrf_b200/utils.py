@@ -9,6 +9,14 @@ from numbers import Number
 import numpy as np
 
 
+def pinned_empty(shape, dtype="float32"):
+    """Addition to the reference's utils: an uninitialised numpy array in page-locked host memory, so
+    that setUnaryEnergy / addPairwiseBilateral upload it by DMA at full PCIe rate."""
+    from ._core import pinned_empty as _pe
+
+    return _pe(shape, dtype)
+
+
 def unary_from_labels(labels, n_labels, gt_prob, zero_unsure=True):
     """Unary energies from a hard label map (reference: utils.py:6-46).
 
