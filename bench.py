@@ -150,7 +150,7 @@ def dist_selftest():
         owned = [units]
     barrier(dist, torch)
     if rank == 0:
-        print(json.dumps({"world": world, "ms": ms, "max_units": total, "owned": owned}))
+        _emit({"world": world, "ms": ms, "max_units": total, "owned": owned})
     if dist is not None:
         dist.destroy_process_group()
 
@@ -304,7 +304,7 @@ def run_b200(args):
         barrier(dist, torch)
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(out))
+        _emit(out)
 
 
 def _ref_model(po, which, img, U):
@@ -364,16 +364,30 @@ def run_reference(args):
     ms = t / args.steps * 1e3
     v = W * H / (ms * 1e-3) / 1e6
     sample = "1 mean-field iteration (stepInference) of the 1080p workload per step, 1 host core; lattice init %.1f s untimed" % t_init
-    print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+    _emit({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
                       "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
                       "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                       "config": {"workload": WORKLOAD, "image": "smooth synthetic (seed=0)"},
                       "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "reference" if which == "ref" else "port",
                                        "sample": sample},
-                      "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+                      "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+
+
+def _emit(obj):
+    """The contract is ONE JSON line on stdout.  Libraries (NCCL's version banner, ...) write to fd 1 behind
+    Python's back, so main() points fd 1 at stderr for the whole run and this writes to the saved fd."""
+    line = (json.dumps(obj) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, line)
+
+
+_REAL_STDOUT = None
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
