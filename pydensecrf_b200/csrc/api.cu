@@ -302,8 +302,12 @@ const float* run_filter(Ctx cx, const Lattice& lt, RowLayout rl, const float* in
   launch_splat(cx, lt, rl, in, pre_norm, A);
   float *src = A, *dst = B;
   for (int j = 0; j <= lt.d; j++) {  // forward axis order: reverse=false everywhere on the inference path
-    launch_blur(cx, lt, rl, j, src, dst);
-    std::swap(src, dst);
+    if (rl.C <= 32 && lt.nchains[j] > 0) {
+      launch_blur_chain(cx, lt, rl, j, src);  // in place
+    } else {
+      launch_blur(cx, lt, rl, j, src, dst);
+      std::swap(src, dst);
+    }
   }
   return src;
 }

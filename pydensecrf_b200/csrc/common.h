@@ -139,6 +139,12 @@ struct Lattice {
   CsrEntry* csr = nullptr;     // [E]
   int2* nbr = nullptr;         // [(d+1)*V] rows (id+1) of the -/+ neighbours, 0 = absent
   int* order = nullptr;        // [V] splat work order: windows of 4096 vertex ids, inside a window by CSR row length
+  // blur chains: along axis j the vertices form disjoint paths v -> n+(v) -> ...; a path that is walked by one
+  // thread group can be blurred IN PLACE (one read + one write per vertex instead of three reads + one write)
+  int* chain_vid = nullptr;    // [(d+1)*V] vertex ids, path by path, per axis
+  int* chain_start = nullptr;  // per axis nchains+1 prefix offsets into that axis' V entries
+  std::vector<int> nchains;    // per axis; 0 = axis not eligible (paths too long / too few): ping-pong blur
+  std::vector<size_t> chain_off;  // per axis offset into chain_start
   int16_t* keys = nullptr;     // [V*d]
   float alpha = 1.f;           // 1/(1+2^-d)
   int max_row = 0;             // longest CSR row (diagnostic)
@@ -155,6 +161,8 @@ void lattice_build(Ctx cx, const FeatureSource& src, int d, int N, Lattice* out)
 void launch_splat(Ctx cx, const Lattice& lt, RowLayout rl, const float* in, const float* pre_norm, float* val);
 // one Jacobi blur pass along axis j: dst = src + 0.5*(src[n1] + src[n2])
 void launch_blur(Ctx cx, const Lattice& lt, RowLayout rl, int axis, const float* src, float* dst);
+// in-place variant over the axis' chains (only when lt.nchains[axis] > 0)
+void launch_blur_chain(Ctx cx, const Lattice& lt, RowLayout rl, int axis, float* val);
 
 enum SliceMode { SLICE_WRITE = 0, SLICE_ACC_FIRST = 1, SLICE_ACC_NEXT = 2 };
 struct CompatDev {

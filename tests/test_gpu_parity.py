@@ -319,6 +319,33 @@ def test_fused_equals_staged_and_deterministic(dcrf):
     assert np.allclose(res[0].sum(0), 1.0, atol=1e-5)
 
 
+def test_chain_blur_forced_small(po):
+    """The in-place chain blur is normally used only for lattices with many short paths; force it on small
+    inputs (fresh process: the threshold is read once) and demand bit-equality with the oracle filter."""
+    import subprocess
+    import sys
+
+    code = r"""
+import os, sys, numpy as np
+sys.path.insert(0, %r)
+os.environ["DCRF_B200_CHAIN_MIN"] = "1"
+import pydensecrf_b200.densecrf as dcrf
+from oracle import pyoracle as po
+rng = np.random.default_rng(3)
+for d, N, scale in [(5, 20001, 2.0), (2, 5000, 3.0), (3, 777, 1.0), (5, 4096, 0.3), (1, 640, 4.0)]:
+    f = (rng.standard_normal((d, N)) * scale).astype(np.float32)
+    o = po.Lattice(f, "orc")
+    m = dcrf.DenseCRF(N, 1)
+    m.addPairwiseEnergy(f, 1.0)
+    for L in (1, 2, 3, 21, 37):
+        x = rng.standard_normal((N, L)).astype(np.float32)
+        assert np.array_equal(m._lattice_filter(0, x), o.filter(x)), (d, N, L)
+print("chain-ok")
+""" % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "chain-ok" in r.stdout, r.stdout + r.stderr
+
+
 def test_fast_softmax_mode_within_tolerance(dcrf, po):
     """setSoftmaxMode(True) trades the bit-faithful softmax for an ex2-based one; it must still meet
     north_star's 1e-4 / MAP bar (held to 2e-5 here)."""
