@@ -520,7 +520,14 @@ void build_impl(Ctx cx, const ElevateParams& ep, Lattice* L) {
   // blur chains per axis (see Lattice::chain_vid)
   L->nchains.assign(dp1, 0);
   L->chain_off.assign(dp1, 0);
-  if (V > 0) {
+  // Measured on B200 (profiles/r01f_chain_blur.txt): the in-place walk halves the row accesses but the 82 MB
+  // bilateral buffer still does not stay in L2 between passes and the walk is latency bound, so it is no faster
+  // than the ping-pong kernel (40 vs 37 us per pass).  Off unless $DCRF_B200_CHAIN_MIN asks for it.
+  static const int min_chains = [] {
+    const char* e = std::getenv("DCRF_B200_CHAIN_MIN");
+    return e ? std::atoi(e) : 0;
+  }();
+  if (V > 0 && min_chains > 0) {
     LaunchScope ls(cx.prof, s, "lattice_chains");
     L->chain_vid = dev_alloc<int>((size_t)dp1 * V, s);
     L->chain_start = dev_alloc<int>((size_t)dp1 * ((size_t)V + 1), s);
@@ -550,11 +557,6 @@ void build_impl(Ctx cx, const ElevateParams& ep, Lattice* L) {
       DCRF_CUDA(cudaMemcpyAsync(&nh, cpos + V, sizeof(int), cudaMemcpyDeviceToHost, s));
       DCRF_CUDA(cudaStreamSynchronize(s));
       // worth it only when there are enough independent paths to fill the GPU
-      // ($DCRF_B200_CHAIN_MIN overrides the threshold; the tests use it to force either path)
-      static const int min_chains = [] {
-        const char* e = std::getenv("DCRF_B200_CHAIN_MIN");
-        return e ? std::atoi(e) : 16384;
-      }();
       if (nh < min_chains) continue;
       k_chain_heads<<<blocks_for(V), kThreads, 0, s>>>(V, cflag, cpos, heads);
       DCRF_CUDA(cudaMemsetAsync(dflag, 0, sizeof(int), s));
