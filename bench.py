@@ -274,9 +274,15 @@ def run_b200(args):
         kern[name] = {"launches_per_step": cnt / args.steps, "avg_ms": avg, "share": tms / tot if tot else None,
                       "alg_bytes": b, "gbs": (b / (avg * 1e-3) / 1e9) if b and avg > 0 else None}
     top = next(iter(kern))
+    traffic = None
+    try:  # DRAM bytes per launch of the same kernel from the committed ncu --set full capture (profiles/traffic.json)
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[top]["dram_bytes_per_launch"]
+    except Exception:
+        pass
     b_stage = wl.stage_bytes_per_iter(N, L, lat) * N_ITER
     roofline = {"bound": "hbm", "kernel": top, "achieved": kern[top]["gbs"], "peak": hbm_peak, "unit": "GB/s",
-                "frac": (kern[top]["gbs"] / hbm_peak) if kern[top]["gbs"] else None, "traffic": None,
+                "frac": (kern[top]["gbs"] / hbm_peak) if kern[top]["gbs"] else None, "traffic": traffic,
+                "traffic_source": "profiles/traffic.json (ncu --set full capture of this kernel on this workload)" if traffic else None,
                 "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)" if peak_src == "measured" else "fallback 6650",
                 "timing": "CUDA events around every launch on the engine's stream, separate instrumented pass of the same K steps",
                 "kernels": kern,
