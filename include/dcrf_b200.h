@@ -170,6 +170,11 @@ dcrf_status dcrf_set_iteration_mode(dcrf_t* m, int mode);
  * so Q equals the reference's to the last bit except for rare last-ulp differences in the L%4 tail labels;
  * 1 = fast softmax in the fused kernel: ex2-based exp, tree sum, reciprocal multiply (~1e-6 relative). */
 dcrf_status dcrf_set_softmax_mode(dcrf_t* m, int fast);
+/* MatrixCompatibility::apply (labelcompatibility.cpp:82-84), out = W*Q per pixel:
+ * 0 (default) = tcgen05 tensor cores with 3xTF32 split operands from 64 labels up (~1e-6 relative), the exact-order
+ *               CUDA-core kernel below that; 1 = always the exact-order kernel (Eigen's GEBP summation order, bit
+ *               faithful); 2 = tensor cores whenever the shape allows (16 <= labels <= 256). */
+dcrf_status dcrf_set_matrix_mode(dcrf_t* m, int mode);
 
 #ifdef __cplusplus
 }

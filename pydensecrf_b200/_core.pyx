@@ -63,6 +63,7 @@ cdef extern from "dcrf_b200.h" nogil:
     int dcrf_pairwise_apply(dcrf_t* m, int k, dcrf_mat_t* Q, dcrf_mat_t** out)
     int dcrf_set_iteration_mode(dcrf_t* m, int mode)
     int dcrf_set_softmax_mode(dcrf_t* m, int fast)
+    int dcrf_set_matrix_mode(dcrf_t* m, int mode)
     int dcrf_host_alloc(size_t nbytes, void** out)
     void dcrf_host_free(void* p, size_t nbytes)
 
@@ -521,6 +522,11 @@ cdef class DenseCRF:
     def setSoftmaxMode(self, bint fast):
         """False (default): bit-faithful softmax; True: faster approximate softmax (~1e-6 relative)."""
         _check(dcrf_set_softmax_mode(self._h, 1 if fast else 0))
+
+    def setMatrixCompatMode(self, int mode):
+        """0 (default): tensor cores (3xTF32) for MatrixCompatibility from 64 labels up; 1: always the
+        bit-faithful exact-order kernel; 2: tensor cores whenever the label count allows (16..256)."""
+        _check(dcrf_set_matrix_mode(self._h, mode))
 
     def _num_pairwise(self):
         return dcrf_num_pairwise(self._h)

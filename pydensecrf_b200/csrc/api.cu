@@ -194,6 +194,7 @@ struct Term {
   float potts_w = 0.f;
   float* diag = nullptr;  // Lp floats
   float* Wm = nullptr;    // L*L floats, symmetrised
+  float *Whi = nullptr, *Wlo = nullptr;  // tf32 split of Wm, zero padded (tensor-core path)
   float *valA = nullptr, *valB = nullptr;  // (V+1) x Lp ping-pong value buffers
   bool pre() const { return ntype == DCRF_NORMALIZE_SYMMETRIC || ntype == DCRF_NORMALIZE_BEFORE; }
   bool post() const { return ntype == DCRF_NORMALIZE_SYMMETRIC || ntype == DCRF_NORMALIZE_AFTER; }
@@ -211,6 +212,7 @@ struct dcrf_model {
   double* kl_sums = nullptr;
   int iter_mode = 0;
   bool fast_softmax = false;
+  int matrix_mode = 0;  // 0: tensor cores from 64 labels up, 1: always the exact-order kernel, 2: tensor cores whenever possible
   cudaEvent_t t0 = nullptr, t1 = nullptr;
   char* flush_buf = nullptr;
   size_t flush_bytes = 0;
@@ -277,7 +279,8 @@ dcrf_model* model_new(int N, int L, int W, int H, int device) {
 void term_free(dcrf_model* m, Term* t) {
   cudaStream_t s = m->stream;
   t->lat.release(s);
-  for (void* p : {(void*)t->norm, (void*)t->diag, (void*)t->Wm, (void*)t->valA, (void*)t->valB}) dev_free(p, s);
+  for (void* p : {(void*)t->norm, (void*)t->diag, (void*)t->Wm, (void*)t->Whi, (void*)t->Wlo, (void*)t->valA, (void*)t->valB})
+    dev_free(p, s);
   delete t;
 }
 
@@ -340,7 +343,11 @@ void term_apply(dcrf_model* m, Term* t, const float* Q, int mode, bool neg_unary
     ensure_scratch(m);
     DCRF_REQUIRE(out != m->msg, "internal: matrix term needs msg as scratch");
     launch_slice(cx, t->lat, m->rl, fin, t->post() ? t->norm : nullptr, nullptr, SLICE_WRITE, nullptr, false, m->msg);
-    launch_matrix_compat(cx, m->rl, m->N, t->Wm, m->msg, mode, m->U, neg_unary, out);
+    const bool tc = t->Whi && (m->matrix_mode == 2 || (m->matrix_mode == 0 && m->L >= 64));
+    if (tc)
+      launch_matrix_compat_tc(cx, m->rl, m->N, t->Whi, t->Wlo, m->msg, mode, m->U, neg_unary, out);
+    else
+      launch_matrix_compat(cx, m->rl, m->N, t->Wm, m->msg, mode, m->U, neg_unary, out);
   }
 }
 
@@ -516,6 +523,13 @@ void add_term(dcrf_model* m, const FeatureSource& src, int d, int compat_kind, c
         for (int b = 0; b < L; b++) w[(size_t)a * L + b] = 0.5f * (compat[(size_t)a * L + b] + compat[(size_t)b * L + a]);
       t->Wm = dev_alloc<float>((size_t)L * L, s);
       DCRF_CUDA(cudaMemcpyAsync(t->Wm, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+      if (matrix_tc_supported(m->rl)) {
+        int Np, Kp;
+        matrix_tc_dims(m->rl, &Np, &Kp);
+        t->Whi = dev_alloc<float>((size_t)Np * Kp, s);
+        t->Wlo = dev_alloc<float>((size_t)Np * Kp, s);
+        launch_split_w(cx, m->rl, t->Wm, t->Whi, t->Wlo);
+      }
       DCRF_CUDA(cudaStreamSynchronize(s));
     }
     // norm_ = lattice_.compute(ones)  (pairwise.cpp:44): a 1-label pass, which takes the seqCompute arithmetic
@@ -1035,6 +1049,12 @@ dcrf_status dcrf_set_iteration_mode(dcrf_t* m, int mode) {
   return guarded([&] {
     DCRF_REQUIRE(m && mode >= 0 && mode <= 2, "bad iteration mode");
     m->iter_mode = mode;
+  });
+}
+dcrf_status dcrf_set_matrix_mode(dcrf_t* m, int mode) {
+  return guarded([&] {
+    DCRF_REQUIRE(m && mode >= 0 && mode <= 2, "bad matrix compatibility mode");
+    m->matrix_mode = mode;
   });
 }
 dcrf_status dcrf_set_softmax_mode(dcrf_t* m, int fast) {

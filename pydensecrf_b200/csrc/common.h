@@ -206,6 +206,13 @@ void launch_init_acc(Ctx cx, RowLayout rl, int N, const float* U, bool neg_unary
 void launch_matrix_compat(Ctx cx, RowLayout rl, int N, const float* W, const float* msg, int mode, const float* U,
                           bool neg_unary, float* out);
 
+// tensor-core (tcgen05, 3xTF32) MatrixCompatibility (matrix_tc.cu)
+bool matrix_tc_supported(RowLayout rl);
+void matrix_tc_dims(RowLayout rl, int* Np, int* Kp);
+void launch_split_w(Ctx cx, RowLayout rl, const float* W, float* hi, float* lo);
+void launch_matrix_compat_tc(Ctx cx, RowLayout rl, int N, const float* Bhi, const float* Blo, const float* msg, int mode,
+                             const float* U, bool neg_unary, float* out);
+
 // layout conversion at the boundary
 void launch_planes_to_rows(Ctx cx, RowLayout rl, int N, const float* planes_LxN, float* rows_NxLp);
 void launch_unpack_rows(Ctx cx, RowLayout rl, int N, const float* packed_NxL, float* rows_NxLp);

@@ -235,6 +235,41 @@ def test_mid_golden(dcrf):
     assert np.array_equal(d.currentMap(Qm)[sure], g["ref_MAP"][sure])
 
 
+@pytest.mark.parametrize("L,W,H", [(150, 67, 45), (64, 50, 40), (21, 64, 48), (250, 31, 29)])
+def test_matrix_compat_tensor_cores(dcrf, po, L, W, H):
+    """MatrixCompatibility on tcgen05 (3xTF32 split operands, fp32 accumulation in TMEM): default from 64 labels
+    up, forced here for the smaller ones.  Not bit-faithful (summation order / split precision), so it is held to
+    5e-6 on one message and 2e-5 on Q after 4 iterations -- still 5x inside north_star's 1e-4."""
+    from tests import workloads as wl
+    import pydensecrf_b200.eigen as eigen
+
+    rng = np.random.default_rng(L)
+    img = wl.smooth_image(H, W, seed=L, grid=8)
+    U = wl.softmax_unary(H, W, L, seed=L, grid=8)
+    Mx = wl.matrix_compat(L, seed=L)
+    d = dcrf.DenseCRF2D(W, H, L)
+    d.setMatrixCompatMode(2)
+    e = dcrf.DenseCRF2D(W, H, L)
+    e.setMatrixCompatMode(1)
+    o = po.CRF((W, H), L, "orc")
+    for c in (d, e, o):
+        c.setUnaryEnergy(U)
+        c.addPairwiseGaussian((3, 2), Mx)
+        c.addPairwiseBilateral((30, 25), (13, 11, 9), img, 5.0)
+    Qo = o.inference(4)
+    Qe = np.array(e.inference(4))
+    Qt = np.array(d.inference(4))
+    assert np.abs(Qe - Qo).max() <= Q_ATOL          # exact-order kernel: bit-faithful as before
+    err = np.abs(Qt - Qo).max()
+    print("tensor-core matrix compat L=%d: max|dQ| = %.3e" % (L, err))
+    assert err <= 2e-5
+    _check_map(Qt, Qo)
+    # one application of the pairwise term on its own
+    Q0 = eigen.matrixXf(np.ascontiguousarray(Qo))
+    mt, me = np.array(d._pairwise_apply(0, Q0)), np.array(e._pairwise_apply(0, Q0))
+    assert np.abs(mt - me).max() <= 5e-6 * max(1.0, np.abs(me).max())
+
+
 @pytest.mark.parametrize("L,W,H", [(2, 64, 48), (3, 50, 34), (7, 61, 47), (21, 128, 96), (150, 40, 30), (33, 31, 29)])
 def test_inference_vs_oracle(dcrf, po, L, W, H):
     from tests import workloads as wl
@@ -246,6 +281,7 @@ def test_inference_vs_oracle(dcrf, po, L, W, H):
     Dg = (-rng.random(L) * 3).astype(np.float32)
     for cg, cb in [(3.0, 10.0), (Dg, Mx), (Mx, 5.0)]:
         d = dcrf.DenseCRF2D(W, H, L)
+        d.setMatrixCompatMode(1)   # exact-order kernel: this test is about bit-faithful arithmetic
         o = po.CRF((W, H), L, "orc")
         for c in (d, o):
             c.setUnaryEnergy(U)
