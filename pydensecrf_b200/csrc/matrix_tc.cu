@@ -12,10 +12,10 @@
 // kernel (filter.cu: k_matrix_compat_tiled) stays the default; this path is chosen for L >= 64 unless the caller
 // asks for bit-faithful arithmetic.
 //
-// One CTA (128 threads) per SM walks 128-pixel tiles.  K is consumed in slabs of 32 (four k-steps), double
+// One CTA (512 threads) per SM walks 128-pixel tiles.  K is consumed in slabs of 32 (four k-steps), double
 // buffered: all threads load + split the slab into the canonical no-swizzle K-major core-matrix layout in shared
 // memory, one thread issues the 12 MMAs of the slab and commits them to an mbarrier that frees the buffer.  The
-// epilogue reads the accumulator with tcgen05.ld (thread t owns TMEM lane t = pixel t of the tile), applies
+// epilogue reads the accumulator with tcgen05.ld (a warp reads TMEM lanes 32*(warp%4).. = 32 pixels), applies
 // tmp1 -= out (or writes out) and stores the row.
 #include <algorithm>
 
@@ -26,7 +26,7 @@ namespace {
 
 constexpr int kTM = 128;  // pixels per tile = UMMA M
 constexpr int kKS = 32;   // K elements per slab
-constexpr int kTCThreads = 128;
+constexpr int kTCThreads = 512;  // 16 warps fill the slabs; warps w, w+4, w+8, .. share TMEM lane quarter w%4 in the epilogue
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -161,9 +161,12 @@ __global__ void __launch_bounds__(kTCThreads, 1) k_matrix_compat_tc(TCArgs a) {
     // ---- epilogue: TMEM lane t = pixel p0 + t ---------------------------------------------------------------
     mbar_wait(smem_u32(bars + 2), tl & 1);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int i = p0 + tid;
-    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
-    for (int c0 = 0; c0 < a.Lp; c0 += 16) {
+    const int lane_q = warp & 3;                 // TMEM lane quarter this warp may read
+    const int i = p0 + lane_q * 32 + (tid & 31);  // pixel of this thread's TMEM lane
+    const uint32_t taddr = tmem + ((uint32_t)(lane_q * 32) << 16);
+    const int nchunk = (a.Lp + 15) / 16, per = (nchunk + kTCThreads / 128 - 1) / (kTCThreads / 128);
+    const int cbeg = (warp >> 2) * per * 16, cend = min(a.Lp, ((warp >> 2) + 1) * per * 16);
+    for (int c0 = cbeg; c0 < cend; c0 += 16) {
       uint32_t r[16];
       asm volatile(
           "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
