@@ -8,6 +8,7 @@
 // and the Eigen-backed matrix objects of pydensecrf/eigen.pyx.  Everything lattice- or label-sized
 // lives in HBM for the life of the model; one CUDA stream per model; no CPU compute path.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -195,7 +196,8 @@ struct Term {
   float* diag = nullptr;  // Lp floats
   float* Wm = nullptr;    // L*L floats, symmetrised
   float *Whi = nullptr, *Wlo = nullptr;  // tf32 split of Wm, zero padded (tensor-core path)
-  float *valA = nullptr, *valB = nullptr;  // (V+1) x Lp ping-pong value buffers
+  float *valA = nullptr, *valB = nullptr;  // (V+1) x Lp ping-pong value buffers (one allocation)
+  size_t val_bytes = 0;
   bool pre() const { return ntype == DCRF_NORMALIZE_SYMMETRIC || ntype == DCRF_NORMALIZE_BEFORE; }
   bool post() const { return ntype == DCRF_NORMALIZE_SYMMETRIC || ntype == DCRF_NORMALIZE_AFTER; }
 };
@@ -221,6 +223,20 @@ struct dcrf_model {
   std::vector<cudaEvent_t> aux_done;
   cudaEvent_t fork = nullptr;
   bool overlap_terms = true;
+  // CUDA graphs of whole inference(n) calls, keyed by everything a captured launch sequence depends on
+  struct GraphEntry {
+    const float* q;
+    int n_iter;
+    cudaGraphExec_t exec;
+    int64_t launches;
+  };
+  std::vector<GraphEntry> graphs;
+  bool use_graphs = true;
+  void drop_graphs() {
+    for (auto& g : graphs)
+      if (g.exec) cudaGraphExecDestroy(g.exec);
+    graphs.clear();
+  }
   Ctx cx() { return Ctx{stream, &prof}; }
 };
 
@@ -273,13 +289,14 @@ dcrf_model* model_new(int N, int L, int W, int H, int device) {
   DCRF_CUDA(cudaEventCreate(&m->t0));
   DCRF_CUDA(cudaEventCreate(&m->t1));
   m->kl_sums = dev_alloc<double>(3, m->stream);
+  m->use_graphs = std::getenv("DCRF_B200_NO_GRAPHS") == nullptr;
   return m;
 }
 
 void term_free(dcrf_model* m, Term* t) {
   cudaStream_t s = m->stream;
   t->lat.release(s);
-  for (void* p : {(void*)t->norm, (void*)t->diag, (void*)t->Wm, (void*)t->Whi, (void*)t->Wlo, (void*)t->valA, (void*)t->valB})
+  for (void* p : {(void*)t->norm, (void*)t->diag, (void*)t->Wm, (void*)t->Whi, (void*)t->Wlo, (void*)t->valA})
     dev_free(p, s);
   delete t;
 }
@@ -287,11 +304,11 @@ void term_free(dcrf_model* m, Term* t) {
 void ensure_val(dcrf_model* m, Term* t) {
   if (t->valA) return;
   const size_t n = ((size_t)t->lat.V + 1) * m->rl.Lp;
-  t->valA = dev_alloc<float>(n, m->stream);
-  t->valB = dev_alloc<float>(n, m->stream);
+  t->valA = dev_alloc<float>(2 * n, m->stream);  // one allocation: A | B
+  t->valB = t->valA + n;
   // row 0 (absent neighbour) must read as zero forever; the kernels never write it
-  DCRF_CUDA(cudaMemsetAsync(t->valA, 0, n * sizeof(float), m->stream));
-  DCRF_CUDA(cudaMemsetAsync(t->valB, 0, n * sizeof(float), m->stream));
+  DCRF_CUDA(cudaMemsetAsync(t->valA, 0, 2 * n * sizeof(float), m->stream));
+  t->val_bytes = 2 * n * sizeof(float);
 }
 void ensure_scratch(dcrf_model* m) {
   const size_t n = (size_t)m->N * m->rl.Lp;
@@ -351,6 +368,20 @@ void term_apply(dcrf_model* m, Term* t, const float* Q, int mode, bool neg_unary
   }
 }
 
+void ensure_scratch_if_staged(dcrf_model* m);
+
+void ensure_aux(dcrf_model* m, int nterms) {
+  while ((int)m->aux.size() < nterms - 1) {
+    cudaStream_t s2;
+    cudaEvent_t e2;
+    DCRF_CUDA(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+    DCRF_CUDA(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+    m->aux.push_back(s2);
+    m->aux_done.push_back(e2);
+  }
+  if (!m->fork) DCRF_CUDA(cudaEventCreateWithFlags(&m->fork, cudaEventDisableTiming));
+}
+
 // one mean-field update of Q in place (the loop body of densecrf.cpp:122-129 / :187-200)
 void mf_step(dcrf_model* m, float* Q, bool neg_unary) {
   Ctx cx = m->cx();
@@ -367,15 +398,7 @@ void mf_step(dcrf_model* m, float* Q, bool neg_unary) {
     // per-launch profiling wants clean, serialised durations: no overlap while it is on
     const bool overlap = m->overlap_terms && a.nterms > 1 && !m->prof.enabled;
     if (overlap) {
-      while ((int)m->aux.size() < a.nterms - 1) {
-        cudaStream_t s2;
-        cudaEvent_t e2;
-        DCRF_CUDA(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
-        DCRF_CUDA(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
-        m->aux.push_back(s2);
-        m->aux_done.push_back(e2);
-      }
-      if (!m->fork) DCRF_CUDA(cudaEventCreateWithFlags(&m->fork, cudaEventDisableTiming));
+      ensure_aux(m, a.nterms);
       DCRF_CUDA(cudaEventRecord(m->fork, m->stream));
     }
     for (int k = 0; k < a.nterms; k++) {
@@ -407,6 +430,13 @@ void mf_step(dcrf_model* m, float* Q, bool neg_unary) {
       term_apply(m, m->terms[k], Q, k == 0 ? SLICE_ACC_FIRST : SLICE_ACC_NEXT, neg_unary, m->acc);
     launch_softmax(cx, m->rl, m->N, m->acc, Q);
   }
+}
+
+void ensure_scratch_if_staged(dcrf_model* m) {
+  const bool fuse = m->iter_mode == 2 || (m->iter_mode == 0 && can_fuse(m));
+  if (!fuse || !(m->iter_mode != 1 && fused_update_supported(m->rl) && (uint64_t)m->N * m->rl.Lp < (1ull << 31))) ensure_scratch(m);
+  for (Term* t : m->terms)
+    if (t->ckind == DCRF_COMPAT_MATRIX) ensure_scratch(m);
 }
 
 // Q0 = expAndNormalize(-unary) (densecrf.cpp:120)
@@ -567,6 +597,7 @@ void add_term(dcrf_model* m, const FeatureSource& src, int d, int compat_kind, c
     throw;
   }
   m->terms.push_back(t);
+  m->drop_graphs();
 }
 
 dcrf_mat* new_result_mat(dcrf_model* m) {
@@ -615,6 +646,7 @@ void dcrf_destroy(dcrf_t* m) {
     for (Term* t : m->terms) term_free(m, t);
     for (void* p : {(void*)m->U, (void*)m->acc, (void*)m->msg, (void*)m->kl_sums, (void*)m->flush_buf}) dev_free(p, m->stream);
     cudaStreamSynchronize(m->stream);
+    m->drop_graphs();
     for (cudaStream_t s2 : m->aux) cudaStreamDestroy(s2);
     for (cudaEvent_t e2 : m->aux_done) cudaEventDestroy(e2);
     if (m->fork) cudaEventDestroy(m->fork);
@@ -633,7 +665,10 @@ dcrf_status dcrf_set_unary_const(dcrf_t* m, const float* u_LxN) {
     DeviceGuard g(m->device);
     const size_t n = (size_t)m->N * m->L;
     float* planes = upload_tmp(m, u_LxN, n * sizeof(float));
-    if (!m->U) m->U = dev_alloc<float>((size_t)m->N * m->rl.Lp, m->stream);
+    if (!m->U) {
+      m->U = dev_alloc<float>((size_t)m->N * m->rl.Lp, m->stream);
+      m->drop_graphs();
+    }
     launch_planes_to_rows(m->cx(), m->rl, m->N, planes, m->U);
     dev_free(planes, m->stream);
     DCRF_CUDA(cudaGetLastError());
@@ -646,7 +681,10 @@ dcrf_status dcrf_set_unary_logistic(dcrf_t* m, const float* Lmat_LxF, int F, con
     DeviceGuard g(m->device);
     float* dL = upload_tmp(m, Lmat_LxF, (size_t)m->L * F * sizeof(float));
     float* df = upload_tmp(m, f_FxN, (size_t)F * m->N * sizeof(float));
-    if (!m->U) m->U = dev_alloc<float>((size_t)m->N * m->rl.Lp, m->stream);
+    if (!m->U) {
+      m->U = dev_alloc<float>((size_t)m->N * m->rl.Lp, m->stream);
+      m->drop_graphs();
+    }
     launch_logistic_unary(m->cx(), m->rl, m->N, F, dL, df, m->U);
     dev_free(dL, m->stream);
     dev_free(df, m->stream);
@@ -717,8 +755,50 @@ dcrf_status dcrf_inference_into(dcrf_t* m, int n_iterations, dcrf_mat_t* Q) {
     DeviceGuard g(m->device);
     mat_reset(Q, m->L, m->N);
     float* q = mat_device(m, Q, false);
-    mf_init(m, q);
-    for (int it = 0; it < n_iterations; it++) mf_step(m, q, true);
+    // everything the launches need is allocated up front, so the sequence below is capturable
+    for (Term* t : m->terms) ensure_val(m, t);
+    ensure_scratch_if_staged(m);
+    ensure_aux(m, (int)m->terms.size());
+    if (m->use_graphs && !m->prof.enabled && n_iterations > 0) {
+      dcrf_model::GraphEntry* hit = nullptr;
+      for (auto& g : m->graphs)
+        if (g.q == q && g.n_iter == n_iterations) hit = &g;
+      if (!hit) {
+        // first call with this (Q, n): run directly and only remember the key -- capturing and instantiating a
+        // graph costs more than it saves for one-shot models (a fresh model per image, cfg 4)
+        if (m->graphs.size() >= 8) m->drop_graphs();
+        m->graphs.push_back({q, n_iterations, nullptr, 0});
+        mf_init(m, q);
+        for (int it = 0; it < n_iterations; it++) mf_step(m, q, true);
+      } else {
+        if (!hit->exec) {  // second call: capture the launch sequence (side streams included) once
+          const int64_t l0 = m->prof.launches;
+          cudaGraph_t graph = nullptr;
+          DCRF_CUDA(cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal));
+          try {
+            mf_init(m, q);
+            for (int it = 0; it < n_iterations; it++) mf_step(m, q, true);
+          } catch (...) {
+            cudaStreamEndCapture(m->stream, &graph);
+            if (graph) cudaGraphDestroy(graph);
+            throw;
+          }
+          DCRF_CUDA(cudaStreamEndCapture(m->stream, &graph));
+          cudaGraphExec_t exec = nullptr;
+          cudaError_t ge = cudaGraphInstantiate(&exec, graph, 0);
+          cudaGraphDestroy(graph);
+          if (ge != cudaSuccess) fail_cuda(ge, "cudaGraphInstantiate", __FILE__, __LINE__);
+          hit->exec = exec;
+          hit->launches = m->prof.launches - l0;
+          m->prof.launches = l0;  // the capture itself launched nothing; replays are counted below
+        }
+        DCRF_CUDA(cudaGraphLaunch(hit->exec, m->stream));
+        m->prof.launches += hit->launches;
+      }
+    } else {
+      mf_init(m, q);
+      for (int it = 0; it < n_iterations; it++) mf_step(m, q, true);
+    }
     DCRF_CUDA(cudaGetLastError());
     mat_written(m, Q);
   });
@@ -1049,18 +1129,21 @@ dcrf_status dcrf_set_iteration_mode(dcrf_t* m, int mode) {
   return guarded([&] {
     DCRF_REQUIRE(m && mode >= 0 && mode <= 2, "bad iteration mode");
     m->iter_mode = mode;
+    m->drop_graphs();
   });
 }
 dcrf_status dcrf_set_matrix_mode(dcrf_t* m, int mode) {
   return guarded([&] {
     DCRF_REQUIRE(m && mode >= 0 && mode <= 2, "bad matrix compatibility mode");
     m->matrix_mode = mode;
+    m->drop_graphs();
   });
 }
 dcrf_status dcrf_set_softmax_mode(dcrf_t* m, int fast) {
   return guarded([&] {
     DCRF_REQUIRE(m, "null argument");
     m->fast_softmax = fast != 0;
+    m->drop_graphs();
   });
 }
 
