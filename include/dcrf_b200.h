@@ -71,6 +71,10 @@ dcrf_status dcrf_set_unary_const(dcrf_t* m, const float* u_LxN);
  * (unary.cpp:48-52: U = Lmat * f).   Lmat: L x F row-major, f: F x N row-major. */
 dcrf_status dcrf_set_unary_logistic(dcrf_t* m, const float* Lmat_LxF, int F, const float* f_FxN);
 
+/* pydensecrf.utils.unary_from_softmax (utils.py:55-79) fused into the upload: U = -log(clip(scale*p +
+ * (1-scale)/L, clip, 1)).  sm: LxN row-major class probabilities; scale <= 0 means "no scale", clip <= 0 "no clip". */
+dcrf_status dcrf_set_unary_from_softmax(dcrf_t* m, const float* sm_LxN, float scale, float clip);
+
 /* ---- pairwise terms (each builds one permutohedral lattice on the GPU) ------------------------- */
 /* replaces addPairwiseEnergy(c_matrixXf(features), _labelcomp(compat), kernel, normalization)
  *                                                      pydensecrf/densecrf.pyx:75 (densecrf.cpp:54; pairwise.cpp:116-122,40-62;
@@ -85,6 +89,14 @@ dcrf_status dcrf_add_pairwise_gaussian(dcrf_t* m, float sx, float sy, int compat
 dcrf_status dcrf_add_pairwise_bilateral(dcrf_t* m, float sx, float sy, float sr, float sg, float sb,
                                         const uint8_t* rgb_HxWx3, int compat_kind, const float* compat_data,
                                         int kernel_type, int norm_type);
+
+/* pydensecrf.utils.create_pairwise_gaussian / create_pairwise_bilateral (utils.py:89-162) + addPairwiseEnergy
+ * with the features generated on the device: nsp spatial coordinates (C order over dims[], prod(dims) = nvar) divided
+ * by sdims[], followed by nch channels of a channel-last image (N x nch, uint8 or float32) divided by schan[].
+ * nch = 0 gives the Gaussian (position-only) kernel.  Bit-identical to feeding the numpy-built features. */
+dcrf_status dcrf_add_pairwise_nd(dcrf_t* m, int nsp, const int* dims, const float* sdims, int nch, const float* schan,
+                                 const void* img, int img_is_float, int compat_kind, const float* compat_data,
+                                 int kernel_type, int norm_type);
 
 /* ---- inference -------------------------------------------------------------------------------- */
 /* replaces eigen.MatrixXf().wrap(_this.inference(niter))   pydensecrf/densecrf.pyx:92 (densecrf.cpp:115-131)

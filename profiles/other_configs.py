@@ -44,6 +44,11 @@ if "cfg5" in which:
     ms = d._timer_stop() / 5
     print("cfg5 256^3 L=2 4-D bilateral FULL_KERNEL 5 iters: numpy features %.0f ms, unary upload %.0f ms, lattice %.0f ms (V=%d), inference(5) %.2f ms -> %.0f MVox*iter/s"
           % (tf, tu, ta, d._lattice_info(0)[2], ms, D ** 3 * 5 / ms / 1e3))
+    d2 = dcrf.DenseCRF(D ** 3, L)
+    d2.setUnaryEnergy(U)
+    _, tb = tm(lambda: (d2.addPairwiseBilateralND((3, 3, 3), (13,), vol, compat=4, chdim=-1, kernel=dcrf.FULL_KERNEL), d2.synchronize()))
+    same = np.array_equal(np.array(d2.inference(5)), np.array(d.inference(5)))
+    print("cfg5 with addPairwiseBilateralND (features built on the device, 16.8 MB uploaded instead of 268 MB): lattice %.0f ms, Q identical: %s" % (tb, same))
     del d, Q
 
 if "cfg3" in which:

@@ -31,6 +31,9 @@ cdef extern from "dcrf_b200.h" nogil:
     void dcrf_destroy(dcrf_t* m)
     int dcrf_set_unary_const(dcrf_t* m, const float* u)
     int dcrf_set_unary_logistic(dcrf_t* m, const float* Lmat, int F, const float* f)
+    int dcrf_set_unary_from_softmax(dcrf_t* m, const float* sm, float scale, float clip)
+    int dcrf_add_pairwise_nd(dcrf_t* m, int nsp, const int* dims, const float* sdims, int nch, const float* schan,
+                             const void* img, int img_is_float, int ckind, const float* cdata, int ktype, int ntype)
     int dcrf_add_pairwise_energy(dcrf_t* m, const float* feat, int d, int ckind, const float* cdata, int ktype, int ntype)
     int dcrf_add_pairwise_gaussian(dcrf_t* m, float sx, float sy, int ckind, const float* cdata, int ktype, int ntype)
     int dcrf_add_pairwise_bilateral(dcrf_t* m, float sx, float sy, float sr, float sg, float sb, const uint8_t* rgb,
@@ -460,6 +463,82 @@ cdef class DenseCRF:
         return out
 
     # ---- additions (not in the reference's wrapper) ------------------------------------------------
+    def setUnaryFromSoftmax(self, sm, scale=None, clip=1e-5):
+        """utils.unary_from_softmax(sm, scale, clip) + setUnaryEnergy in one call, evaluated on the GPU while the
+        probabilities are uploaded (SURVEY 8f-2).  `sm`: class probabilities, classes on axis 0."""
+        import numpy as np
+        a = np.ascontiguousarray(np.asarray(sm, dtype=np.float32).reshape(sm.shape[0], -1))
+        if a.shape[0] != self._nlabel or a.shape[1] != self._nvar:
+            raise ValueError("Bad shape for softmax (Need {}, got {})".format((self._nlabel, self._nvar), (a.shape[0], a.shape[1])))
+        if scale is not None and not (0 < scale <= 1):
+            raise ValueError("`scale` needs to be in (0,1]")
+        cdef float[:, ::1] v = a
+        cdef float sc = -1.0 if scale is None else scale
+        cdef float cl = -1.0 if clip is None else clip
+        cdef int st
+        with nogil:
+            st = dcrf_set_unary_from_softmax(self._h, &v[0, 0], sc, cl)
+        _check(st)
+
+    def _add_nd(self, sdims, schan, img, chdim, compat, kernel, normalization, shape):
+        import numpy as np
+        cdef _Compat c = _Compat(compat, self._nlabel)
+        cdef int kt = int(KernelType(kernel)), nt = int(NormalizationType(normalization)), st
+        nch = 0
+        flat = None
+        if img is not None:
+            im = np.asarray(img)
+            if chdim == -1:
+                im = im[..., np.newaxis]
+            else:
+                im = np.moveaxis(im, chdim, -1)
+            nd = im.ndim                 # (no negative indices: this module is compiled with wraparound=False)
+            shape = im.shape[:nd - 1]
+            nch = im.shape[nd - 1]
+            if im.dtype != np.uint8:
+                im = im.astype(np.float32)
+            flat = np.ascontiguousarray(im.reshape(-1, nch))
+            if isinstance(schan, Number):
+                schan = [schan] * nch
+            if len(schan) != nch:
+                raise ValueError("need one `schan` entry per channel ({}), got {}".format(nch, len(schan)))
+        shape = tuple([int(x) for x in shape])
+        if len(sdims) != len(shape):
+            raise ValueError("need one `sdims` entry per spatial axis ({}), got {}".format(len(shape), len(sdims)))
+        if int(np.prod(shape)) != self._nvar:
+            raise ValueError("Bad shape for pairwise energy (shape {} has {} elements, need {})".format(shape, int(np.prod(shape)), self._nvar))
+        d_arr = np.ascontiguousarray(shape, dtype=np.int32)
+        s_arr = np.ascontiguousarray(sdims, dtype=np.float32)
+        c_arr = np.ascontiguousarray(schan if nch else [0.0], dtype=np.float32)
+        cdef int[::1] dv = d_arr
+        cdef float[::1] sv = s_arr
+        cdef float[::1] cv = c_arr
+        cdef const float* cp = c.data()
+        cdef int nsp = len(shape), nc = nch, isf = 0
+        cdef const void* ip = NULL
+        cdef unsigned char[:, ::1] u8
+        cdef float[:, ::1] f32
+        if nch:
+            if flat.dtype == np.uint8:
+                u8 = flat
+                ip = <const void*>&u8[0, 0]
+            else:
+                f32 = flat
+                ip = <const void*>&f32[0, 0]
+                isf = 1
+        with nogil:
+            st = dcrf_add_pairwise_nd(self._h, nsp, &dv[0], &sv[0], nc, &cv[0], ip, isf, c.kind, cp, kt, nt)
+        _check(st)
+
+    def addPairwiseGaussianND(self, sdims, shape, compat, kernel=DIAG_KERNEL, normalization=NORMALIZE_SYMMETRIC):
+        """addPairwiseEnergy(utils.create_pairwise_gaussian(sdims, shape), ...) with the features generated on the GPU."""
+        self._add_nd(sdims, None, None, -1, compat, kernel, normalization, shape)
+
+    def addPairwiseBilateralND(self, sdims, schan, img, compat, chdim=-1, kernel=DIAG_KERNEL, normalization=NORMALIZE_SYMMETRIC):
+        """addPairwiseEnergy(utils.create_pairwise_bilateral(sdims, schan, img, chdim), ...) with the features generated on
+        the GPU: only the image (uint8 or float32) is uploaded instead of the (n_spatial + n_channels) x N float matrix."""
+        self._add_nd(sdims, schan, img, chdim, compat, kernel, normalization, None)
+
     def inferenceInto(self, int niter, MatrixXf Q not None):
         """inference(niter) written into an existing MatrixXf (no allocation when shapes match)."""
         cdef dcrf_mat_t* q = Q.handle()

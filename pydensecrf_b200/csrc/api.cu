@@ -675,6 +675,23 @@ dcrf_status dcrf_set_unary_const(dcrf_t* m, const float* u_LxN) {
     DCRF_CUDA(cudaStreamSynchronize(m->stream));  // the caller may free/overwrite u now
   });
 }
+dcrf_status dcrf_set_unary_from_softmax(dcrf_t* m, const float* sm_LxN, float scale, float clip) {
+  return guarded([&] {
+    DCRF_REQUIRE(m && sm_LxN, "null argument");
+    DCRF_REQUIRE(!(scale > 1.f), "`scale` needs to be in (0,1]");
+    DeviceGuard g(m->device);
+    const size_t n = (size_t)m->N * m->L;
+    float* planes = upload_tmp(m, sm_LxN, n * sizeof(float));
+    if (!m->U) {
+      m->U = dev_alloc<float>((size_t)m->N * m->rl.Lp, m->stream);
+      m->drop_graphs();
+    }
+    launch_softmax_planes_to_unary(m->cx(), m->rl, m->N, planes, scale, clip, m->U);
+    dev_free(planes, m->stream);
+    DCRF_CUDA(cudaGetLastError());
+    DCRF_CUDA(cudaStreamSynchronize(m->stream));
+  });
+}
 dcrf_status dcrf_set_unary_logistic(dcrf_t* m, const float* Lmat_LxF, int F, const float* f_FxN) {
   return guarded([&] {
     DCRF_REQUIRE(m && Lmat_LxF && f_FxN && F >= 1, "bad argument");
@@ -745,6 +762,46 @@ dcrf_status dcrf_add_pairwise_bilateral(dcrf_t* m, float sx, float sy, float sr,
       throw;
     }
     dev_free(im, m->stream);
+  });
+}
+
+dcrf_status dcrf_add_pairwise_nd(dcrf_t* m, int nsp, const int* dims, const float* sdims, int nch, const float* schan,
+                                 const void* img, int img_is_float, int compat_kind, const float* compat_data,
+                                 int kernel_type, int norm_type) {
+  return guarded([&] {
+    DCRF_REQUIRE(m && dims && sdims, "null argument");
+    DCRF_REQUIRE(nsp >= 1 && nsp <= kMaxNdAxes && nch >= 0 && nch <= kMaxNdAxes, "at most 6 spatial axes and 6 channels");
+    DCRF_REQUIRE(nch == 0 || (schan && img), "channels given without an image");
+    int64_t total = 1;
+    for (int k = 0; k < nsp; k++) {
+      DCRF_REQUIRE(dims[k] >= 1, "bad shape");
+      total *= dims[k];
+    }
+    DCRF_REQUIRE(total == m->N, "shape has " + std::to_string(total) + " elements, model has " + std::to_string(m->N) + " variables");
+    DeviceGuard g(m->device);
+    FeatureSource src{};
+    src.kind = FEAT_ND;
+    src.nsp = nsp, src.nch = nch, src.img_is_float = img_is_float;
+    int st = 1;
+    for (int k = nsp - 1; k >= 0; k--) {
+      src.dims[k] = dims[k];
+      src.stride[k] = st;
+      st *= dims[k];
+      src.sdims[k] = sdims[k];
+    }
+    for (int c = 0; c < nch; c++) src.schan[c] = schan[c];
+    void* dimg = nullptr;
+    if (nch > 0) {
+      dimg = upload_tmp(m, img, (size_t)m->N * nch * (img_is_float ? 4 : 1));
+      src.img = dimg;
+    }
+    try {
+      add_term(m, src, nsp + nch, compat_kind, compat_data, kernel_type, norm_type);
+    } catch (...) {
+      dev_free(dimg, m->stream);
+      throw;
+    }
+    dev_free(dimg, m->stream);
   });
 }
 

@@ -122,13 +122,22 @@ struct CsrEntry {  // one contribution to a vertex, rows sorted by (pixel, corne
   float w;
 };
 
-enum FeatureKind { FEAT_GENERIC = 0, FEAT_GAUSS2D = 1, FEAT_BILATERAL2D = 2 };
+enum FeatureKind { FEAT_GENERIC = 0, FEAT_GAUSS2D = 1, FEAT_BILATERAL2D = 2, FEAT_ND = 3 };
+static const int kMaxNdAxes = 6;
 struct FeatureSource {
   int kind;
   const float* feat;  // device, d x N row-major (FEAT_GENERIC)
   const uint8_t* rgb; // device, N x 3 (FEAT_BILATERAL2D)
   int W;
   float s[5];         // sx, sy, sr, sg, sb
+  // FEAT_ND: what utils.create_pairwise_gaussian / create_pairwise_bilateral build on the host (utils.py:89-162):
+  // nsp spatial coordinates (C order over dims[]) / sdims, then nch channels of a channel-last image / schan
+  int nsp, nch, img_is_float;
+  int dims[kMaxNdAxes];
+  int stride[kMaxNdAxes];
+  float sdims[kMaxNdAxes];
+  float schan[kMaxNdAxes];
+  const void* img;    // device, N x nch, uint8 or float32
 };
 
 struct Lattice {
@@ -215,6 +224,9 @@ void launch_matrix_compat_tc(Ctx cx, RowLayout rl, int N, const float* Bhi, cons
 
 // layout conversion at the boundary
 void launch_planes_to_rows(Ctx cx, RowLayout rl, int N, const float* planes_LxN, float* rows_NxLp);
+// same transposition with utils.unary_from_softmax (utils.py:55-79) applied on the way: -log(clip(scale*p + (1-scale)/L))
+void launch_softmax_planes_to_unary(Ctx cx, RowLayout rl, int N, const float* planes_LxN, float scale, float clip,
+                                    float* rows_NxLp);
 void launch_unpack_rows(Ctx cx, RowLayout rl, int N, const float* packed_NxL, float* rows_NxLp);
 void launch_pack_rows(Ctx cx, RowLayout rl, int N, const float* rows_NxLp, float* packed_NxL);
 void launch_fill(Ctx cx, float* p, size_t n, float v);

@@ -46,6 +46,12 @@ struct ElevateParams {
 
 __device__ __forceinline__ float feature_of(const FeatureSource& s, int k, int i, int N) {
   if (s.kind == FEAT_GENERIC) return __ldg(s.feat + (size_t)k * N + i);
+  if (s.kind == FEAT_ND) {
+    if (k < s.nsp) return __fdiv_rn((float)((i / s.stride[k]) % s.dims[k]), s.sdims[k]);
+    const size_t e = (size_t)i * s.nch + (k - s.nsp);
+    const float v = s.img_is_float ? __ldg(static_cast<const float*>(s.img) + e) : (float)__ldg(static_cast<const uint8_t*>(s.img) + e);
+    return __fdiv_rn(v, s.schan[k - s.nsp]);
+  }
   // DenseCRF2D::addPairwiseGaussian / Bilateral (densecrf.cpp:61-81): int coordinate / byte divided
   // by the float sigma, pixel index = y*W + x
   if (k == 0) return __fdiv_rn((float)(i % s.W), s.s[0]);

@@ -382,6 +382,54 @@ print("chain-ok")
     assert r.returncode == 0 and "chain-ok" in r.stdout, r.stdout + r.stderr
 
 
+def test_nd_feature_builders_match_numpy_features(dcrf):
+    """addPairwiseBilateralND / addPairwiseGaussianND build utils.create_pairwise_* features on the device; the
+    lattices must be bit-identical to the ones built from the numpy features."""
+    from pydensecrf_b200 import utils
+
+    rng = np.random.default_rng(12)
+    cases = [
+        (rng.integers(0, 255, (9, 11, 13), dtype=np.uint8), -1, (3, 2.5, 2), (13,)),            # volume, no channel axis
+        (rng.integers(0, 255, (24, 31, 3), dtype=np.uint8), 2, (5, 4), (13, 11, 9)),            # RGB, channel last
+        (rng.random((2, 19, 23)).astype(np.float32) * 40, 0, (3, 3), 7.0),                      # float, channel first, scalar schan
+    ]
+    for img, chdim, sdims, schan in cases:
+        f = utils.create_pairwise_bilateral(sdims=sdims, schan=schan, img=img, chdim=chdim)
+        N = f.shape[1]
+        a, b = dcrf.DenseCRF(N, 3), dcrf.DenseCRF(N, 3)
+        a.addPairwiseEnergy(f, compat=2.0)
+        b.addPairwiseBilateralND(sdims, schan, img, compat=2.0, chdim=chdim)
+        for x, y in zip(a._lattice_dump(0), b._lattice_dump(0)):
+            assert np.array_equal(x, y)
+        shape = tuple(np.delete(img.shape, chdim)) if chdim != -1 else img.shape
+        g = utils.create_pairwise_gaussian(sdims=sdims, shape=shape)
+        a, b = dcrf.DenseCRF(N, 3), dcrf.DenseCRF(N, 3)
+        a.addPairwiseEnergy(g, compat=2.0)
+        b.addPairwiseGaussianND(sdims, shape, compat=2.0)
+        for x, y in zip(a._lattice_dump(0), b._lattice_dump(0)):
+            assert np.array_equal(x, y)
+    with pytest.raises(ValueError):
+        dcrf.DenseCRF(100, 2).addPairwiseGaussianND((3, 3), (9, 9), compat=1.0)
+
+
+def test_unary_from_softmax_on_device(dcrf):
+    """setUnaryFromSoftmax == utils.unary_from_softmax + setUnaryEnergy, up to the last ulp of log."""
+    from pydensecrf_b200 import utils
+
+    rng = np.random.default_rng(13)
+    W, H, L = 40, 30, 5
+    sm = np.ascontiguousarray(rng.dirichlet(np.ones(L) * 0.3, W * H).T, dtype=np.float32).reshape(L, H, W)
+    sm[0, 0, :5] = 0.0
+    for scale, clip in [(None, 1e-5), (0.7, 1e-5), (0.5, None)]:
+        a, b = dcrf.DenseCRF2D(W, H, L), dcrf.DenseCRF2D(W, H, L)
+        a.setUnaryEnergy(utils.unary_from_softmax(sm, scale=scale, clip=clip))
+        b.setUnaryFromSoftmax(sm, scale=scale, clip=clip)
+        for c in (a, b):
+            c.addPairwiseGaussian(3, 3.0)
+        qa, qb = np.array(a.inference(3)), np.array(b.inference(3))
+        assert np.abs(qa - qb).max() <= 1e-6, (scale, clip)
+
+
 def test_fast_softmax_mode_within_tolerance(dcrf, po):
     """setSoftmaxMode(True) trades the bit-faithful softmax for an ex2-based one; it must still meet
     north_star's 1e-4 / MAP bar (held to 2e-5 here)."""
