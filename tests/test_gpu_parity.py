@@ -102,6 +102,36 @@ def test_lattice_ties_phantoms_and_duplicates(dcrf, po):
         assert np.array_equal(m._lattice_filter(0, x), o.filter(x))
 
 
+@pytest.mark.parametrize("d,N,scale", [(12, 700, 1.0), (32, 300, 0.7), (2, 4000, 3.0e4), (5, 3000, 9.0e3)])
+def test_lattice_edge_dims_and_key_wrap(dcrf, po, d, N, scale):
+    """Feature dimensions beyond the templated ones (generic path up to 32) and coordinates large enough that
+    the int16 vertex keys wrap (the reference truncates keys to short)."""
+    rng = np.random.default_rng(d + N)
+    f = (rng.standard_normal((d, N)) * scale).astype(np.float32)
+    o = po.Lattice(f, "orc")
+    m = _lattice_of(dcrf, f)
+    off, bary, keys, nbr, _ = m._lattice_dump(0)
+    ooff, obary, _, onbr = o.dump()
+    assert m._lattice_info(0)[2] == o.V
+    assert np.array_equal(keys, o.keys())
+    assert np.array_equal(off, ooff) and np.array_equal(bary, obary) and np.array_equal(nbr, onbr)
+    x = rng.standard_normal((N, 3)).astype(np.float32)
+    assert np.array_equal(m._lattice_filter(0, x), o.filter(x))
+
+
+def test_single_label_and_single_variable(dcrf, po):
+    rng = np.random.default_rng(0)
+    for N, L in [(1, 3), (7, 1), (2, 2)]:
+        f = rng.standard_normal((2, N)).astype(np.float32)
+        U = rng.random((L, N)).astype(np.float32)
+        d = dcrf.DenseCRF(N, L)
+        o = po.CRF(N, L, "orc")
+        for c in (d, o):
+            c.setUnaryEnergy(U)
+            c.addPairwiseEnergy(f, 2.0)
+        assert np.abs(np.array(d.inference(3)) - o.inference(3)).max() <= Q_ATOL
+
+
 def test_lattice_2d_builders_exact(dcrf, po):
     from tests import workloads as wl
 
