@@ -11,6 +11,15 @@ if ROOT not in sys.path:
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
     config.addinivalue_line("markers", "slow: larger CPU case (still part of the default CPU suite)")
+    # the product is a compiled library: build it in-tree if this checkout has not been built yet
+    # (nvcc cross-compiles for sm_100a without a GPU; a no-op when everything is up to date)
+    import glob
+
+    pkg = os.path.join(ROOT, "pydensecrf_b200")
+    if not (os.path.exists(os.path.join(pkg, "libdcrf_b200.so")) and glob.glob(os.path.join(pkg, "_core*.so"))):
+        import __graft_entry__
+
+        __graft_entry__.build()
 
 
 @pytest.fixture(scope="session")
