@@ -161,7 +161,9 @@ def kernel_bytes(name, lat):
     out = {}
     for (d, V) in lat:
         out.setdefault("splat", []).append(4 * N * L + 8 * N * (d + 1) + 4 * V * L)
-        out.setdefault("blur", []).extend([2 * 4 * V * L + 8 * V] * (d + 1))
+        # d+1 axes: two per launch ("blur2": twice the one-axis bytes of the stage model), a single one if d+1 is odd
+        out.setdefault("blur2", []).extend([2 * (2 * 4 * V * L + 8 * V)] * ((d + 1) // 2))
+        out.setdefault("blur", []).extend([2 * 4 * V * L + 8 * V] * ((d + 1) % 2))
     # fused update: slice of every kernel (vertex values + offsets/weights) + read U + write Q; the
     # K messages never reach HBM
     out["fused_update"] = [sum(4 * V * L + 8 * N * (d + 1) for d, V in lat) + 2 * 4 * N * L]

@@ -320,10 +320,19 @@ void ensure_scratch(dcrf_model* m) {
 const float* run_filter(Ctx cx, const Lattice& lt, RowLayout rl, const float* in, const float* pre_norm, float* A,
                         float* B) {
   launch_splat(cx, lt, rl, in, pre_norm, A);
+  // two axes per launch by default (measured 7.89 -> 7.50 ms per 1080p inference); DCRF_B200_BLUR2=0 turns it off
+  static const int pair_blur = [] {
+    const char* e = std::getenv("DCRF_B200_BLUR2");
+    return e ? std::atoi(e) : 1;
+  }();
   float *src = A, *dst = B;
   for (int j = 0; j <= lt.d; j++) {  // forward axis order: reverse=false everywhere on the inference path
     if (rl.C <= 32 && lt.nchains[j] > 0) {
       launch_blur_chain(cx, lt, rl, j, src);  // in place
+    } else if (pair_blur && j + 1 <= lt.d && lt.nchains[j + 1] == 0 && lt.V >= pair_blur) {
+      launch_blur2(cx, lt, rl, j, src, dst);  // axes j and j+1 together
+      std::swap(src, dst);
+      j++;
     } else {
       launch_blur(cx, lt, rl, j, src, dst);
       std::swap(src, dst);

@@ -385,6 +385,33 @@ def test_fused_equals_staged_and_deterministic(dcrf):
     assert np.allclose(res[0].sum(0), 1.0, atol=1e-5)
 
 
+def test_single_axis_blur_path(po):
+    """Blur runs two axes per launch by default; with DCRF_B200_BLUR2=0 every axis is its own launch.  Both must
+    reproduce the oracle filter bit for bit (fresh process: the switch is read once)."""
+    import subprocess
+    import sys
+
+    code = r"""
+import os, sys, numpy as np
+sys.path.insert(0, %r)
+os.environ["DCRF_B200_BLUR2"] = "0"
+import pydensecrf_b200.densecrf as dcrf
+from oracle import pyoracle as po
+rng = np.random.default_rng(4)
+for d, N in [(5, 9001), (2, 3000), (4, 777)]:
+    f = (rng.standard_normal((d, N)) * 2.0).astype(np.float32)
+    o = po.Lattice(f, "orc")
+    m = dcrf.DenseCRF(N, 1)
+    m.addPairwiseEnergy(f, 1.0)
+    for L in (1, 2, 21):
+        x = rng.standard_normal((N, L)).astype(np.float32)
+        assert np.array_equal(m._lattice_filter(0, x), o.filter(x)), (d, N, L)
+print("single-ok")
+""" % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "single-ok" in r.stdout, r.stdout + r.stderr
+
+
 def test_chain_blur_forced_small(po):
     """The in-place chain blur is normally used only for lattices with many short paths; force it on small
     inputs (fresh process: the threshold is read once) and demand bit-equality with the oracle filter."""
