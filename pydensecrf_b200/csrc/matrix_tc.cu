@@ -12,11 +12,12 @@
 // kernel (filter.cu: k_matrix_compat_tiled) stays the default; this path is chosen for L >= 64 unless the caller
 // asks for bit-faithful arithmetic.
 //
-// One CTA (512 threads) per SM walks 128-pixel tiles.  K is consumed in slabs of 32 (four k-steps), double
+// Up to two CTAs (512 threads each) per SM walk 128-pixel tiles.  K is consumed in slabs of 16 (two k-steps), double
 // buffered: all threads load + split the slab into the canonical no-swizzle K-major core-matrix layout in shared
-// memory, one thread issues the 12 MMAs of the slab and commits them to an mbarrier that frees the buffer.  The
-// epilogue reads the accumulator with tcgen05.ld (a warp reads TMEM lanes 32*(warp%4).. = 32 pixels), applies
-// tmp1 -= out (or writes out) and stores the row.
+// memory, one thread issues the 6 MMAs of the slab and commits them to an mbarrier that frees the buffer.  The
+// epilogue reads the accumulator with tcgen05.ld (a warp reads TMEM lanes 32*(warp%4).. = 32 pixels) into a
+// shared-memory tile that aliases the operand stages, then all threads apply tmp1 -= out (or write out) with
+// coalesced row accesses.
 #include <algorithm>
 
 #include "common.h"
@@ -25,7 +26,8 @@ namespace dcrf {
 namespace {
 
 constexpr int kTM = 128;  // pixels per tile = UMMA M
-constexpr int kKS = 32;   // K elements per slab
+constexpr int kKS = 16;   // K elements per slab (two k-steps): small stages so that two CTAs fit on an SM
+constexpr int kCH = kKS / 4;  // 16-byte K chunks per slab
 constexpr int kTCThreads = 512;  // 16 warps fill the slabs; warps w, w+4, w+8, .. share TMEM lane quarter w%4 in the epilogue
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -77,14 +79,15 @@ struct TCArgs {
   float* out;
 };
 
-__global__ void __launch_bounds__(kTCThreads, 1) k_matrix_compat_tc(TCArgs a) {
+__global__ void __launch_bounds__(kTCThreads, 2) k_matrix_compat_tc(TCArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5;
   const uint32_t lboA = kTM * 16 + 16, lboB = (uint32_t)a.Np * 16 + 16;  // +16: spreads the K chunks over the banks
-  const uint32_t szA = 8 * lboA, szB = 8 * lboB;
+  const uint32_t szA = kCH * lboA, szB = kCH * lboB;
   const uint32_t stage_bytes = 2 * szA + 2 * szB;
   uint8_t* stage0 = smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * stage_bytes);  // [0,1]: stage free, [2]: accumulator done
+  const uint32_t tile_bytes = (uint32_t)(kTM * (a.Lp + 4) * sizeof(float));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + max(2 * stage_bytes, tile_bytes));  // [0,1]: stage free, [2]: accumulator done
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
 
   if (tid == 0) {
@@ -118,9 +121,10 @@ __global__ void __launch_bounds__(kTCThreads, 1) k_matrix_compat_tc(TCArgs a) {
       const int k0 = s * kKS;
       // A slab: 128 rows x 32 floats, thread -> (row, 16-byte chunk c); split into hi/lo on the way
 #pragma unroll
-      for (int pass = 0; pass < (kTM * 8) / kTCThreads; pass++) {
+      for (int pass = 0; pass < (kTM * kCH + kTCThreads - 1) / kTCThreads; pass++) {
         const int e = pass * kTCThreads + tid;
-        const int row = e >> 3, c = e & 7;
+        if (e >= kTM * kCH) break;
+        const int row = e / kCH, c = e % kCH;
         const int k = k0 + c * 4;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p0 + row < a.N && k < a.Lp) v = __ldg(reinterpret_cast<const float4*>(a.msg + (size_t)(p0 + row) * a.Lp + k));
@@ -134,8 +138,8 @@ __global__ void __launch_bounds__(kTCThreads, 1) k_matrix_compat_tc(TCArgs a) {
         *reinterpret_cast<float4*>(sb + szA + o) = l;
       }
       // B slab: Np rows (labels) x 32 floats of the pre-split W
-      for (int e = tid; e < a.Np * 8; e += kTCThreads) {
-        const int row = e >> 3, c = e & 7;
+      for (int e = tid; e < a.Np * kCH; e += kTCThreads) {
+        const int row = e / kCH, c = e % kCH;
         const size_t g = (size_t)row * a.Kp + k0 + c * 4;
         const uint32_t o = (uint32_t)c * lboB + (uint32_t)row * 16;
         *reinterpret_cast<float4*>(sb + 2 * szA + o) = __ldg(reinterpret_cast<const float4*>(a.Bhi + g));
@@ -158,56 +162,70 @@ __global__ void __launch_bounds__(kTCThreads, 1) k_matrix_compat_tc(TCArgs a) {
         if (s == nslabs - 1) umma_commit(smem_u32(bars + 2));  // accumulator complete
       }
     }
-    // ---- epilogue: TMEM lane t = pixel p0 + t ---------------------------------------------------------------
+    // ---- epilogue: accumulator -> shared-memory tile -> coalesced read-modify-write of the output rows ----------
     mbar_wait(smem_u32(bars + 2), tl & 1);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int lane_q = warp & 3;                 // TMEM lane quarter this warp may read
-    const int i = p0 + lane_q * 32 + (tid & 31);  // pixel of this thread's TMEM lane
-    const uint32_t taddr = tmem + ((uint32_t)(lane_q * 32) << 16);
-    const int nchunk = (a.Lp + 15) / 16, per = (nchunk + kTCThreads / 128 - 1) / (kTCThreads / 128);
-    const int cbeg = (warp >> 2) * per * 16, cend = min(a.Lp, ((warp >> 2) + 1) * per * 16);
-    for (int c0 = cbeg; c0 < cend; c0 += 16) {
-      uint32_t r[16];
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-            "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-          : "r"(taddr + (uint32_t)c0));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (i < a.N) {
+    // all MMAs of this tile are complete, so both operand stages are free: the output tile aliases them
+    float* T = reinterpret_cast<float*>(stage0);
+    const int TLD = a.Lp + 4;  // row pitch in floats: 16-byte aligned, 28 mod 32 -> conflict-free float4 stores
+    {
+      const int lane_q = warp & 3;                  // TMEM lane quarter this warp may read
+      const int trow = lane_q * 32 + (tid & 31);     // tile row = TMEM lane
+      const uint32_t taddr = tmem + ((uint32_t)(lane_q * 32) << 16);
+      const int nchunk = (a.Lp + 15) / 16, per = (nchunk + kTCThreads / 128 - 1) / (kTCThreads / 128);
+      const int cbeg = (warp >> 2) * per * 16, cend = min(a.Lp, ((warp >> 2) + 1) * per * 16);
+      for (int c0 = cbeg; c0 < cend; c0 += 16) {
+        uint32_t r[16];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+            : "r"(taddr + (uint32_t)c0));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {
-          const int col = c0 + j;
-          if (col >= a.Lp) break;
-          float o[4] = {__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])};
-          const size_t off = (size_t)i * a.Lp + col;
-          if (a.mode != SLICE_WRITE) {
-            float b[4];
-            if (a.mode == SLICE_ACC_FIRST) {
-              const float z = a.neg_unary ? -0.f : 0.f;
-              if (a.U) {
-                const float4 u = __ldg(reinterpret_cast<const float4*>(a.U + off));
-                b[0] = z - u.x, b[1] = z - u.y, b[2] = z - u.z, b[3] = z - u.w;
-              } else {
-                b[0] = b[1] = b[2] = b[3] = z;
-              }
-            } else {
-              const float4 v = *reinterpret_cast<const float4*>(a.out + off);
-              b[0] = v.x, b[1] = v.y, b[2] = v.z, b[3] = v.w;
-            }
-#pragma unroll
-            for (int q = 0; q < 4; q++) o[q] = b[q] - o[q];
-          }
-#pragma unroll
-          for (int q = 0; q < 4; q++)
-            if (col + q >= a.L) o[q] = 0.f;
-          *reinterpret_cast<float4*>(a.out + off) = make_float4(o[0], o[1], o[2], o[3]);
+          if (c0 + j < a.Lp)
+            *reinterpret_cast<float4*>(T + (size_t)trow * TLD + c0 + j) =
+                make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
         }
       }
     }
-    // every lane has been read: the next tile's first MMA may overwrite the accumulator
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    __syncthreads();  // tile complete in shared memory; TMEM may be overwritten by the next tile's MMAs
+    {
+      const int cpr = a.Lp >> 2;  // float4 chunks per row
+      for (int e = tid; e < kTM * cpr; e += kTCThreads) {
+        const int row = e / cpr, c4 = e - row * cpr;
+        const int i = p0 + row;
+        if (i >= a.N) continue;
+        const int col = c4 * 4;
+        const float4 t4 = *reinterpret_cast<const float4*>(T + (size_t)row * TLD + col);
+        float o[4] = {t4.x, t4.y, t4.z, t4.w};
+        const size_t off = (size_t)i * a.Lp + col;
+        if (a.mode != SLICE_WRITE) {
+          float b[4];
+          if (a.mode == SLICE_ACC_FIRST) {
+            const float z = a.neg_unary ? -0.f : 0.f;
+            if (a.U) {
+              const float4 u = __ldg(reinterpret_cast<const float4*>(a.U + off));
+              b[0] = z - u.x, b[1] = z - u.y, b[2] = z - u.z, b[3] = z - u.w;
+            } else {
+              b[0] = b[1] = b[2] = b[3] = z;
+            }
+          } else {
+            const float4 v = *reinterpret_cast<const float4*>(a.out + off);
+            b[0] = v.x, b[1] = v.y, b[2] = v.z, b[3] = v.w;
+          }
+#pragma unroll
+          for (int q = 0; q < 4; q++) o[q] = b[q] - o[q];
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+          if (col + q >= a.L) o[q] = 0.f;
+        *reinterpret_cast<float4*>(a.out + off) = make_float4(o[0], o[1], o[2], o[3]);
+      }
+    }
+    __syncthreads();  // the output tile has been consumed: the next tile may refill the operand stages
   }
 
   __syncthreads();
@@ -248,15 +266,18 @@ void launch_matrix_compat_tc(Ctx cx, RowLayout rl, int N, const float* Bhi, cons
   a.N = N, a.L = rl.L, a.Lp = rl.Lp, a.mode = mode, a.neg_unary = neg_unary ? 1 : 0;
   matrix_tc_dims(rl, &a.Np, &a.Kp);
   a.msg = msg, a.Bhi = Bhi, a.Blo = Blo, a.U = U, a.out = out;
-  const size_t stage = 2 * (size_t)(8 * (kTM * 16 + 16)) + 2 * (size_t)(8 * (a.Np * 16 + 16));
-  const size_t smem = 2 * stage + 64;
+  const size_t stage = 2 * (size_t)(kCH * (kTM * 16 + 16)) + 2 * (size_t)(kCH * (a.Np * 16 + 16));
+  // the epilogue's output tile (128 x (Lp+4) floats) aliases the operand stages; the barriers sit behind both
+  const size_t body = std::max(2 * stage, (size_t)kTM * (a.Lp + 4) * sizeof(float));
+  const size_t smem = body + 64;
   DCRF_REQUIRE(smem <= 227 * 1024, "too many labels for the tensor-core matrix compatibility kernel");
   DCRF_CUDA(cudaFuncSetAttribute(k_matrix_compat_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int ntiles = (N + kTM - 1) / kTM;
-  k_matrix_compat_tc<<<std::min(ntiles, sms), kTCThreads, smem, cx.stream>>>(a);
+  const int per_sm = (2 * smem + 4096 <= 227 * 1024) ? 2 : 1;  // two CTAs per SM when shared memory (and 2 x 256 TMEM columns) allow
+  k_matrix_compat_tc<<<std::min(ntiles, sms * per_sm), kTCThreads, smem, cx.stream>>>(a);
 }
 
 }  // namespace dcrf
