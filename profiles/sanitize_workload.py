@@ -1,0 +1,26 @@
+"""Small workload for compute-sanitizer (memcheck / racecheck / initcheck): every kernel family once."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import pydensecrf_b200.densecrf as dcrf
+from tests import workloads as wl
+W, H = 67, 45
+img = wl.smooth_image(H, W, seed=1, grid=8)
+for L, compat in [(21, 3.0), (2, 3.0), (5, None), (70, "m"), (150, "m")]:
+    U = wl.softmax_unary(H, W, L, seed=L, grid=8)
+    c = wl.matrix_compat(L) if compat == "m" else (np.linspace(-3, -1, L).astype(np.float32) if compat is None else compat)
+    d = dcrf.DenseCRF2D(W, H, L)
+    d.setUnaryEnergy(U)
+    d.addPairwiseGaussian(3, c)
+    d.addPairwiseBilateral(30, 13, img, c)
+    d.addPairwiseBilateralND((30, 30), (13, 13, 13), img, compat=c, chdim=2)
+    Q = d.inference(2)
+    Q2 = d.inference(2); Q2 = d.inference(2)   # third call replays the CUDA graph
+    kl = d.klDivergence(Q)
+    m = d.currentMap(Q)
+    Qs, a, b = d.startInference(); d.stepInference(Qs, a, b)
+    d.setSoftmaxMode(True); d.inference(1); d.setSoftmaxMode(False)
+    d._set_iteration_mode(1); d.inference(1)
+    print(L, float(np.asarray(Q).sum()), kl, int(m.sum()))
+print("sanitize-ok")
