@@ -326,14 +326,14 @@ def _ref_model(po, which, img, U):
 
 def cpu_baseline(img, U, d):
     """The reference's own C++ (oracle/_ref) -- or the C restatement when it is absent -- on the same
-    1080p input, one host core (the reference is single-threaded), bounded to 5 iterations; the same run
+    1080p input, one host core (the reference is single-threaded), one full inference(10); the same run
     checks the GPU result against it."""
     from oracle import pyoracle as po
 
     which = "ref" if po.available("ref") else "orc"
     if which == "orc" and not po.available("orc"):
         po.build()
-    n = 5
+    n = N_ITER  # the full 10 iterations north_star states the Q tolerance for (about 10 s on one core)
     c, t_init = _ref_model(po, which, img, U)
     t0 = time.perf_counter()
     Qc = c.inference(n)

@@ -487,6 +487,26 @@ def test_unary_from_softmax_on_device(dcrf):
         assert np.abs(qa - qb).max() <= 1e-6, (scale, clip)
 
 
+def test_two_devices_in_one_process(dcrf):
+    """Handles carry their device: two models on two GPUs driven from one process give identical results
+    (replicas only -- SURVEY 8e).  Skipped on single-GPU boxes."""
+    if dcrf.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from tests import workloads as wl
+
+    W, H, L = 96, 64, 21
+    U = wl.softmax_unary(H, W, L, seed=3, grid=8)
+    img = wl.smooth_image(H, W, seed=3, grid=8)
+    res = []
+    for dev in (0, 1):
+        d = dcrf.DenseCRF2D(W, H, L, device=dev)
+        d.setUnaryEnergy(U)
+        d.addPairwiseGaussian(3, 3.0)
+        d.addPairwiseBilateral(80, 13, img, 10.0)
+        res.append(np.array(d.inference(5)))
+    assert np.array_equal(res[0], res[1])
+
+
 def test_fast_softmax_mode_within_tolerance(dcrf, po):
     """setSoftmaxMode(True) trades the bit-faithful softmax for an ex2-based one; it must still meet
     north_star's 1e-4 / MAP bar (held to 2e-5 here)."""
