@@ -112,39 +112,58 @@ __global__ void __launch_bounds__(kTCThreads, 2) k_matrix_compat_tc(TCArgs a) {
   uint32_t it = 0;  // slabs issued so far by this CTA (stage = it & 1)
   uint32_t tl = 0;  // tiles finished by this CTA
 
+  // Register prefetch: the global loads of slab n+1 are issued right after slab n has been stored to shared
+  // memory, so their latency runs under the fence / barrier / MMA issue of slab n (and under the epilogue at a
+  // tile boundary).  kTM * kCH == kTCThreads: one A chunk per thread; B needs up to kNB chunks per thread.
+  static_assert(kTM * kCH == kTCThreads, "one A chunk per thread");
+  constexpr int kNB = (256 * kCH + kTCThreads - 1) / kTCThreads;
+  float4 pa, pbh[kNB], pbl[kNB];
+  const int arow = tid / kCH, ac = tid % kCH;
+  auto prefetch = [&](int tile_p0, int slab) {
+    const int k = slab * kKS + ac * 4;
+    pa = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tile_p0 + arow < a.N && k < a.Lp) pa = __ldg(reinterpret_cast<const float4*>(a.msg + (size_t)(tile_p0 + arow) * a.Lp + k));
+#pragma unroll
+    for (int u = 0; u < kNB; u++) {
+      const int e = u * kTCThreads + tid;
+      if (e < a.Np * kCH) {
+        const size_t g = (size_t)(e / kCH) * a.Kp + slab * kKS + (e % kCH) * 4;
+        pbh[u] = __ldg(reinterpret_cast<const float4*>(a.Bhi + g));
+        pbl[u] = __ldg(reinterpret_cast<const float4*>(a.Blo + g));
+      }
+    }
+  };
+  if ((int)blockIdx.x < ntiles) prefetch(blockIdx.x * kTM, 0);
+
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tl++) {
     const int p0 = tile * kTM;
     for (int s = 0; s < nslabs; s++, it++) {
       const uint32_t st = it & 1;
       uint8_t* sb = stage0 + st * stage_bytes;
       if (it >= 2) mbar_wait(smem_u32(bars + st), ((it >> 1) - 1) & 1);  // MMAs that read this buffer are done
-      const int k0 = s * kKS;
-      // A slab: 128 rows x 32 floats, thread -> (row, 16-byte chunk c); split into hi/lo on the way
-#pragma unroll
-      for (int pass = 0; pass < (kTM * kCH + kTCThreads - 1) / kTCThreads; pass++) {
-        const int e = pass * kTCThreads + tid;
-        if (e >= kTM * kCH) break;
-        const int row = e / kCH, c = e % kCH;
-        const int k = k0 + c * 4;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p0 + row < a.N && k < a.Lp) v = __ldg(reinterpret_cast<const float4*>(a.msg + (size_t)(p0 + row) * a.Lp + k));
+      {  // registers -> shared memory (A split into hi/lo on the way)
         float4 h, l;
-        split_tf32(v.x, h.x, l.x);
-        split_tf32(v.y, h.y, l.y);
-        split_tf32(v.z, h.z, l.z);
-        split_tf32(v.w, h.w, l.w);
-        const uint32_t o = (uint32_t)c * lboA + (uint32_t)row * 16;
+        split_tf32(pa.x, h.x, l.x);
+        split_tf32(pa.y, h.y, l.y);
+        split_tf32(pa.z, h.z, l.z);
+        split_tf32(pa.w, h.w, l.w);
+        const uint32_t o = (uint32_t)ac * lboA + (uint32_t)arow * 16;
         *reinterpret_cast<float4*>(sb + o) = h;
         *reinterpret_cast<float4*>(sb + szA + o) = l;
+#pragma unroll
+        for (int u = 0; u < kNB; u++) {
+          const int e = u * kTCThreads + tid;
+          if (e < a.Np * kCH) {
+            const uint32_t ob = (uint32_t)(e % kCH) * lboB + (uint32_t)(e / kCH) * 16;
+            *reinterpret_cast<float4*>(sb + 2 * szA + ob) = pbh[u];
+            *reinterpret_cast<float4*>(sb + 2 * szA + szB + ob) = pbl[u];
+          }
+        }
       }
-      // B slab: Np rows (labels) x 32 floats of the pre-split W
-      for (int e = tid; e < a.Np * kCH; e += kTCThreads) {
-        const int row = e / kCH, c = e % kCH;
-        const size_t g = (size_t)row * a.Kp + k0 + c * 4;
-        const uint32_t o = (uint32_t)c * lboB + (uint32_t)row * 16;
-        *reinterpret_cast<float4*>(sb + 2 * szA + o) = __ldg(reinterpret_cast<const float4*>(a.Bhi + g));
-        *reinterpret_cast<float4*>(sb + 2 * szA + szB + o) = __ldg(reinterpret_cast<const float4*>(a.Blo + g));
-      }
+      if (s + 1 < nslabs)
+        prefetch(p0, s + 1);
+      else if (tile + (int)gridDim.x < ntiles)
+        prefetch((tile + (int)gridDim.x) * kTM, 0);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA's async proxy
       __syncthreads();
       if (tid == 0) {
