@@ -82,7 +82,9 @@ struct TCArgs {
 __global__ void __launch_bounds__(kTCThreads, 2) k_matrix_compat_tc(TCArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5;
-  const uint32_t lboA = kTM * 16 + 16, lboB = (uint32_t)a.Np * 16 + 16;  // +16: spreads the K chunks over the banks
+  // +32: consecutive K chunks land two 16-byte bank groups apart, so the 2 rows x 4 chunks a quarter-warp stores hit
+  // eight different bank groups (with +16 rows and chunks collide pairwise: 230 M conflicts in profiles/r01j)
+  const uint32_t lboA = kTM * 16 + 32, lboB = (uint32_t)a.Np * 16 + 32;
   const uint32_t szA = kCH * lboA, szB = kCH * lboB;
   const uint32_t stage_bytes = 2 * szA + 2 * szB;
   uint8_t* stage0 = smem;
@@ -285,7 +287,7 @@ void launch_matrix_compat_tc(Ctx cx, RowLayout rl, int N, const float* Bhi, cons
   a.N = N, a.L = rl.L, a.Lp = rl.Lp, a.mode = mode, a.neg_unary = neg_unary ? 1 : 0;
   matrix_tc_dims(rl, &a.Np, &a.Kp);
   a.msg = msg, a.Bhi = Bhi, a.Blo = Blo, a.U = U, a.out = out;
-  const size_t stage = 2 * (size_t)(kCH * (kTM * 16 + 16)) + 2 * (size_t)(kCH * (a.Np * 16 + 16));
+  const size_t stage = 2 * (size_t)(kCH * (kTM * 16 + 32)) + 2 * (size_t)(kCH * (a.Np * 16 + 32));
   // the epilogue's output tile (128 x (Lp+4) floats) aliases the operand stages; the barriers sit behind both
   const size_t body = std::max(2 * stage, (size_t)kTM * (a.Lp + 4) * sizeof(float));
   const size_t smem = body + 64;
