@@ -71,6 +71,10 @@ dcrf_status dcrf_set_unary_const(dcrf_t* m, const float* u_LxN);
  * (unary.cpp:48-52: U = Lmat * f).   Lmat: L x F row-major, f: F x N row-major. */
 dcrf_status dcrf_set_unary_logistic(dcrf_t* m, const float* Lmat_LxF, int F, const float* f_FxN);
 
+/* GPU-resident pipelines: the unary already sits in device memory (e.g. a network's output).  dev_u_LxN: LxN
+ * row-major floats on the model's GPU; no PCIe transfer.  Synchronises the device first (the producer's stream is
+ * not known to this library). */
+dcrf_status dcrf_set_unary_device(dcrf_t* m, const float* dev_u_LxN);
 /* pydensecrf.utils.unary_from_softmax (utils.py:55-79) fused into the upload: U = -log(clip(scale*p +
  * (1-scale)/L, clip, 1)).  sm: LxN row-major class probabilities; scale <= 0 means "no scale", clip <= 0 "no clip". */
 dcrf_status dcrf_set_unary_from_softmax(dcrf_t* m, const float* sm_LxN, float scale, float clip);
@@ -130,6 +134,10 @@ int dcrf_mat_cols(const dcrf_mat_t* a);
  * device copy is newer.  The caller may write through it: call dcrf_mat_release_host() when the view
  * ends so the next device use re-uploads. */
 dcrf_status dcrf_mat_host_ptr(dcrf_mat_t* a, float** ptr);
+/* device view of a result matrix for GPU-resident consumers (exposed as __cuda_array_interface__ by the binding):
+ * cols rows of *pitch_floats floats, the first `rows` of each row are the labels of one variable.  Valid until the
+ * matrix is destroyed or written again; fails if the current contents only exist on the host. */
+dcrf_status dcrf_mat_device_ptr(dcrf_mat_t* a, float** ptr, int* pitch_floats, int* device);
 /* a buffer view ended (the .pyx's __releasebuffer__, pydensecrf/eigen.pyx:97): the host copy may have been written */
 void dcrf_mat_release_host(dcrf_mat_t* a);
 

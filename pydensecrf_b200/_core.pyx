@@ -32,6 +32,8 @@ cdef extern from "dcrf_b200.h" nogil:
     int dcrf_set_unary_const(dcrf_t* m, const float* u)
     int dcrf_set_unary_logistic(dcrf_t* m, const float* Lmat, int F, const float* f)
     int dcrf_set_unary_from_softmax(dcrf_t* m, const float* sm, float scale, float clip)
+    int dcrf_set_unary_device(dcrf_t* m, const float* dev_u)
+    int dcrf_mat_device_ptr(dcrf_mat_t* a, float** ptr, int* pitch, int* device)
     int dcrf_add_pairwise_nd(dcrf_t* m, int nsp, const int* dims, const float* sdims, int nch, const float* schan,
                              const void* img, int img_is_float, int ckind, const float* cdata, int ktype, int ntype)
     int dcrf_add_pairwise_energy(dcrf_t* m, const float* feat, int d, int ckind, const float* cdata, int ktype, int ntype)
@@ -284,6 +286,18 @@ cdef class MatrixXf:
         if self.h != NULL:
             dcrf_mat_release_host(self.h)
 
+    @property
+    def __cuda_array_interface__(self):
+        """Zero-copy device view for GPU-resident consumers (torch.as_tensor(Q, device="cuda"), cupy.asarray(Q)):
+        shape (cols, rows) = (variables, labels), row pitch padded to a multiple of four floats.  Only available
+        while the current contents live on the GPU (i.e. for results of inference / stepInference)."""
+        cdef float* p = NULL
+        cdef int pitch = 0, dev = 0
+        _check(dcrf_mat_device_ptr(self.handle(), &p, &pitch, &dev))
+        self._refresh()
+        return {"shape": (self.shape[1], self.shape[0]), "typestr": "<f4", "data": (<size_t>p, False),
+                "strides": (pitch * 4, 4), "version": 3}
+
 
 def matrixXf(float[:, ::1] arr not None):
     cdef dcrf_mat_t* h = NULL
@@ -463,6 +477,25 @@ cdef class DenseCRF:
         return out
 
     # ---- additions (not in the reference's wrapper) ------------------------------------------------
+    def setUnaryEnergyDevice(self, u):
+        """setUnaryEnergy for a unary that already lives in GPU memory: `u` is any object exposing
+        __cuda_array_interface__ (torch / cupy array), float32, C-contiguous, shape (nlabels, nvar), on the model's
+        device.  No host round trip."""
+        cai = u.__cuda_array_interface__
+        shape = tuple(cai["shape"])
+        if len(shape) != 2 or shape[0] != self._nlabel or shape[1] != self._nvar:
+            raise ValueError("Bad shape for unary energy (Need {}, got {})".format((self._nlabel, self._nvar), shape))
+        if cai["typestr"] not in ("<f4", "=f4", "|f4"):
+            raise ValueError("Buffer dtype mismatch, expected 'float' but got {}".format(cai["typestr"]))
+        st_ = cai.get("strides")
+        if st_ is not None and tuple(st_) != (shape[1] * 4, 4):
+            raise ValueError("device array is not C-contiguous")
+        cdef size_t ptr = cai["data"][0]
+        cdef int st
+        with nogil:
+            st = dcrf_set_unary_device(self._h, <const float*>ptr)
+        _check(st)
+
     def setUnaryFromSoftmax(self, sm, scale=None, clip=1e-5):
         """utils.unary_from_softmax(sm, scale, clip) + setUnaryEnergy in one call, evaluated on the GPU while the
         probabilities are uploaded (SURVEY 8f-2).  `sm`: class probabilities, classes on axis 0."""

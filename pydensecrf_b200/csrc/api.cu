@@ -684,6 +684,25 @@ dcrf_status dcrf_set_unary_const(dcrf_t* m, const float* u_LxN) {
     DCRF_CUDA(cudaStreamSynchronize(m->stream));  // the caller may free/overwrite u now
   });
 }
+dcrf_status dcrf_set_unary_device(dcrf_t* m, const float* dev_u_LxN) {
+  return guarded([&] {
+    DCRF_REQUIRE(m && dev_u_LxN, "null argument");
+    DeviceGuard g(m->device);
+    cudaPointerAttributes at{};
+    DCRF_CUDA(cudaPointerGetAttributes(&at, dev_u_LxN));
+    DCRF_REQUIRE(at.type == cudaMemoryTypeDevice && at.device == m->device,
+                 "setUnaryEnergyDevice needs a device pointer on the model's GPU (device " + std::to_string(m->device) + ")");
+    // the producer (another library's stream) is unknown to this engine: order after everything on the device
+    DCRF_CUDA(cudaDeviceSynchronize());
+    if (!m->U) {
+      m->U = dev_alloc<float>((size_t)m->N * m->rl.Lp, m->stream);
+      m->drop_graphs();
+    }
+    launch_planes_to_rows(m->cx(), m->rl, m->N, dev_u_LxN, m->U);
+    DCRF_CUDA(cudaGetLastError());
+    DCRF_CUDA(cudaStreamSynchronize(m->stream));  // the caller may reuse its buffer now
+  });
+}
 dcrf_status dcrf_set_unary_from_softmax(dcrf_t* m, const float* sm_LxN, float scale, float clip) {
   return guarded([&] {
     DCRF_REQUIRE(m && sm_LxN, "null argument");
@@ -1011,6 +1030,17 @@ dcrf_status dcrf_mat_host_ptr(dcrf_mat_t* a, float** ptr) {
     }
     a->exports++;
     *ptr = a->host;
+  });
+}
+dcrf_status dcrf_mat_device_ptr(dcrf_mat_t* a, float** ptr, int* pitch_floats, int* device) {
+  return guarded([&] {
+    DCRF_REQUIRE(a && ptr && pitch_floats && device, "null argument");
+    DCRF_REQUIRE(a->dev && a->dev_valid, "matrix has no current device copy (it was created or modified on the host)");
+    DeviceGuard g(a->device);
+    if (a->ready) DCRF_CUDA(cudaEventSynchronize(a->ready));  // producer finished: safe for any stream to read
+    *ptr = a->dev;
+    *pitch_floats = RowLayout(a->rows).Lp;
+    *device = a->device;
   });
 }
 void dcrf_mat_release_host(dcrf_mat_t* a) {

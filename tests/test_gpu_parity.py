@@ -507,6 +507,36 @@ def test_two_devices_in_one_process(dcrf):
     assert np.array_equal(res[0], res[1])
 
 
+def test_device_resident_io_with_torch(dcrf):
+    """GPU-resident pipeline: unary taken from a torch CUDA tensor, result read back as a torch view through
+    __cuda_array_interface__; must equal the host path bit for bit."""
+    torch = pytest.importorskip("torch")
+    from tests import workloads as wl
+
+    W, H, L = 96, 64, 21
+    U = wl.softmax_unary(H, W, L, seed=3, grid=8)
+    img = wl.smooth_image(H, W, seed=3, grid=8)
+    res = []
+    for use_dev in (False, True):
+        d = dcrf.DenseCRF2D(W, H, L, device=0)
+        if use_dev:
+            d.setUnaryEnergyDevice(torch.from_numpy(U).cuda(0))
+        else:
+            d.setUnaryEnergy(U)
+        d.addPairwiseGaussian(3, 3.0)
+        d.addPairwiseBilateral(80, 13, img, 10.0)
+        Q = d.inference(5)
+        if use_dev:
+            t = torch.as_tensor(Q, device="cuda:0")          # (N, L) view on the engine's buffer, no copy
+            assert tuple(t.shape) == (W * H, L)
+            res.append(t.cpu().numpy().T)
+        else:
+            res.append(np.array(Q))
+    assert np.array_equal(res[0], res[1])
+    with pytest.raises(ValueError):
+        d.setUnaryEnergyDevice(torch.zeros((L, 5), device="cuda:0"))
+
+
 def test_fast_softmax_mode_within_tolerance(dcrf, po):
     """setSoftmaxMode(True) trades the bit-faithful softmax for an ex2-based one; it must still meet
     north_star's 1e-4 / MAP bar (held to 2e-5 here)."""
