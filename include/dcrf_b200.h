@@ -179,8 +179,9 @@ dcrf_status dcrf_lattice_info(const dcrf_t* m, int k, int* d, int* N, int* V);
 dcrf_status dcrf_lattice_dump(dcrf_t* m, int k, int32_t* offset, float* bary, int16_t* keys, int32_t* nbr,
                               float* norm);
 /* Permutohedral::compute of term k (permutohedral.cpp:596-604) on a host array, NxL pixel-major in/out;
- * no normalisation, no compatibility. */
-dcrf_status dcrf_lattice_filter(dcrf_t* m, int k, const float* in_NxL, int L, float* out_NxL);
+ * no normalisation, no compatibility.  reverse != 0 blurs the axes in descending order (the `reverse` argument of
+ * the reference, used by applyTranspose). */
+dcrf_status dcrf_lattice_filter(dcrf_t* m, int k, const float* in_NxL, int L, int reverse, float* out_NxL);
 /* PairwisePotential::apply of term k (pairwise.cpp:173-178) on a device matrix -> new matrix */
 dcrf_status dcrf_pairwise_apply(dcrf_t* m, int k, dcrf_mat_t* Q, dcrf_mat_t** out);
 /* 0 = pick automatically, 1 = force the staged (unfused) iteration, 2 = force the fused iteration (fails if

@@ -64,7 +64,7 @@ cdef extern from "dcrf_b200.h" nogil:
     int dcrf_num_pairwise(const dcrf_t* m)
     int dcrf_lattice_info(const dcrf_t* m, int k, int* d, int* N, int* V)
     int dcrf_lattice_dump(dcrf_t* m, int k, int32_t* offset, float* bary, int16_t* keys, int32_t* nbr, float* norm)
-    int dcrf_lattice_filter(dcrf_t* m, int k, const float* inp, int L, float* out)
+    int dcrf_lattice_filter(dcrf_t* m, int k, const float* inp, int L, int reverse, float* out)
     int dcrf_pairwise_apply(dcrf_t* m, int k, dcrf_mat_t* Q, dcrf_mat_t** out)
     int dcrf_set_iteration_mode(dcrf_t* m, int mode)
     int dcrf_set_softmax_mode(dcrf_t* m, int fast)
@@ -668,17 +668,18 @@ cdef class DenseCRF:
         _check(st)
         return off, bary, keys[:V], nbr[:, :V], norm
 
-    def _lattice_filter(self, int k, float[:, ::1] x_NxL not None):
+    def _lattice_filter(self, int k, float[:, ::1] x_NxL not None, bint reverse=False):
         """Permutohedral::compute of term k on a (N, L) pixel-major array."""
         import numpy as np
         out = np.empty((x_NxL.shape[0], x_NxL.shape[1]), np.float32)
         cdef float[:, ::1] o = out
         cdef int L = <int>x_NxL.shape[1], st
+        cdef int rev = 1 if reverse else 0
         d, N, V = self._lattice_info(k)
         if x_NxL.shape[0] != N:
             raise ValueError("need (N, L) input with N = {}".format(N))
         with nogil:
-            st = dcrf_lattice_filter(self._h, k, &x_NxL[0, 0], L, &o[0, 0])
+            st = dcrf_lattice_filter(self._h, k, &x_NxL[0, 0], L, rev, &o[0, 0])
         _check(st)
         return out
 

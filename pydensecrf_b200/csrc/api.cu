@@ -316,23 +316,28 @@ void ensure_scratch(dcrf_model* m) {
   if (!m->msg) m->msg = dev_alloc<float>(n, m->stream);
 }
 
-// Permutohedral::compute: splat, d+1 blurs; returns the buffer holding the blurred vertex values
+// Permutohedral::compute: splat, d+1 blurs; returns the buffer holding the blurred vertex values.  Inference
+// always blurs the axes in forward order; reverse = true is Permutohedral::compute(..., reverse) as used by
+// applyTranspose (pairwise.cpp:71-72), reachable through dcrf_lattice_filter for parity checks.
 const float* run_filter(Ctx cx, const Lattice& lt, RowLayout rl, const float* in, const float* pre_norm, float* A,
-                        float* B) {
-  launch_splat(cx, lt, rl, in, pre_norm, A);
+                        float* B, bool reverse = false) {
   // two axes per launch by default (measured 7.89 -> 7.50 ms per 1080p inference); DCRF_B200_BLUR2=0 turns it off
   static const int pair_blur = [] {
     const char* e = std::getenv("DCRF_B200_BLUR2");
     return e ? std::atoi(e) : 1;
   }();
+  launch_splat(cx, lt, rl, in, pre_norm, A);
   float *src = A, *dst = B;
-  for (int j = 0; j <= lt.d; j++) {  // forward axis order: reverse=false everywhere on the inference path
+  const int n = lt.d + 1;
+  for (int i = 0; i < n; i++) {
+    const int j = reverse ? n - 1 - i : i;
+    const int j2 = reverse ? j - 1 : j + 1;  // the axis after j in blur order
     if (rl.C <= 32 && lt.nchains[j] > 0) {
       launch_blur_chain(cx, lt, rl, j, src);  // in place
-    } else if (pair_blur && j + 1 <= lt.d && lt.nchains[j + 1] == 0 && lt.V >= pair_blur) {
-      launch_blur2(cx, lt, rl, j, src, dst);  // axes j and j+1 together
+    } else if (pair_blur && i + 1 < n && lt.nchains[j2] == 0 && lt.V >= pair_blur) {
+      launch_blur2(cx, lt, rl, j, j2, src, dst);  // axes j and j2 together
       std::swap(src, dst);
-      j++;
+      i++;
     } else {
       launch_blur(cx, lt, rl, j, src, dst);
       std::swap(src, dst);
@@ -1170,7 +1175,7 @@ dcrf_status dcrf_lattice_dump(dcrf_t* m, int k, int32_t* offset, float* bary, in
     DCRF_CUDA(cudaStreamSynchronize(s));
   });
 }
-dcrf_status dcrf_lattice_filter(dcrf_t* m, int k, const float* in_NxL, int L, float* out_NxL) {
+dcrf_status dcrf_lattice_filter(dcrf_t* m, int k, const float* in_NxL, int L, int reverse, float* out_NxL) {
   return guarded([&] {
     DCRF_REQUIRE(m && k >= 0 && k < (int)m->terms.size(), "no such pairwise term");
     DCRF_REQUIRE(in_NxL && out_NxL && L >= 1 && L <= 4096, "bad argument");
@@ -1188,7 +1193,7 @@ dcrf_status dcrf_lattice_filter(dcrf_t* m, int k, const float* in_NxL, int L, fl
     float* B = dev_alloc<float>(vn, s);
     DCRF_CUDA(cudaMemsetAsync(A, 0, vn * sizeof(float), s));
     DCRF_CUDA(cudaMemsetAsync(B, 0, vn * sizeof(float), s));
-    const float* fin = run_filter(cx, lt, rl, rows, nullptr, A, B);
+    const float* fin = run_filter(cx, lt, rl, rows, nullptr, A, B, reverse != 0);
     launch_slice(cx, lt, rl, fin, nullptr, nullptr, SLICE_WRITE, nullptr, false, rows);
     launch_pack_rows(cx, rl, N, rows, packed);
     DCRF_CUDA(cudaMemcpyAsync(out_NxL, packed, (size_t)N * L * sizeof(float), cudaMemcpyDeviceToHost, s));

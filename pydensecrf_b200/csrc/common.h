@@ -170,8 +170,8 @@ void lattice_build(Ctx cx, const FeatureSource& src, int d, int N, Lattice* out)
 void launch_splat(Ctx cx, const Lattice& lt, RowLayout rl, const float* in, const float* pre_norm, float* val);
 // one Jacobi blur pass along axis j: dst = src + 0.5*(src[n1] + src[n2])
 void launch_blur(Ctx cx, const Lattice& lt, RowLayout rl, int axis, const float* src, float* dst);
-// axes `axis` and `axis+1` in one launch (bit-identical to two launch_blur calls)
-void launch_blur2(Ctx cx, const Lattice& lt, RowLayout rl, int axis, const float* src, float* dst);
+// axis `axis` then axis `axis2` in one launch (bit-identical to two launch_blur calls)
+void launch_blur2(Ctx cx, const Lattice& lt, RowLayout rl, int axis, int axis2, const float* src, float* dst);
 // in-place variant over the axis' chains (only when lt.nchains[axis] > 0)
 void launch_blur_chain(Ctx cx, const Lattice& lt, RowLayout rl, int axis, float* val);
 

@@ -83,6 +83,7 @@ def test_lattice_random_exact(dcrf, po, d, N, scale):
     for L in (1, 2, 4, 21, 37):
         x = rng.standard_normal((N, L)).astype(np.float32)
         assert np.array_equal(m._lattice_filter(0, x), o.filter(x)), L
+        assert np.array_equal(m._lattice_filter(0, x, reverse=True), o.filter(x, reverse=True)), L
 
 
 def test_lattice_ties_phantoms_and_duplicates(dcrf, po):
