@@ -166,6 +166,11 @@ dcrf_status dcrf_profile_read(dcrf_t* m, dcrf_prof_entry* out, int cap, int* n, 
 int64_t dcrf_launch_count(const dcrf_t* m);
 /* write a >L2-sized scratch buffer on the model's stream (timing hygiene between iterations) */
 dcrf_status dcrf_flush_l2(dcrf_t* m);
+/* Self-test of the restated float arithmetic on the device (test infrastructure): which = 0 compares the packed
+ * two-element restatement of Eigen's pexp with the scalar one for every float in [-100, 0] (n ignored); which = 1
+ * compares the shared-reciprocal column division with IEEE division on n random operand pairs.  *mismatches
+ * receives the number of results whose bits differ (must be 0). */
+dcrf_status dcrf_debug_selftest(dcrf_t* m, int which, uint64_t n, uint64_t seed, uint64_t* mismatches);
 /* upload a host unary into a device-resident matrix / run inference entirely on device buffers:
  * same as dcrf_inference but reuses *Q if it already has the right shape (no allocation in the timed loop) */
 dcrf_status dcrf_inference_into(dcrf_t* m, int n_iterations, dcrf_mat_t* Q);

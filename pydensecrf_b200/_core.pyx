@@ -11,7 +11,7 @@ from numbers import Number
 import enum
 
 from cpython.buffer cimport PyBUF_WRITABLE
-from libc.stdint cimport int16_t, int32_t, int64_t, uint8_t
+from libc.stdint cimport int16_t, int32_t, int64_t, uint8_t, uint64_t
 
 
 cdef extern from "dcrf_b200.h" nogil:
@@ -61,6 +61,7 @@ cdef extern from "dcrf_b200.h" nogil:
     int dcrf_profile_read(dcrf_t* m, dcrf_prof_entry* out, int cap, int* n, int reset)
     int64_t dcrf_launch_count(const dcrf_t* m)
     int dcrf_flush_l2(dcrf_t* m)
+    int dcrf_debug_selftest(dcrf_t* m, int which, uint64_t n, uint64_t seed, uint64_t* mismatches)
     int dcrf_num_pairwise(const dcrf_t* m)
     int dcrf_lattice_info(const dcrf_t* m, int k, int* d, int* N, int* V)
     int dcrf_lattice_dump(dcrf_t* m, int k, int32_t* offset, float* bary, int16_t* keys, int32_t* nbr, float* norm)
@@ -627,6 +628,16 @@ cdef class DenseCRF:
 
     def _flush_l2(self):
         _check(dcrf_flush_l2(self._h))
+
+    def _selftest(self, int which, n=0, seed=0):
+        """Device self-test of the restated arithmetic (0: packed pexp, exhaustive; 1: column division, n random
+        pairs); returns the number of mismatching results."""
+        cdef uint64_t bad = 0, nn = n, sd = seed
+        cdef int st
+        with nogil:
+            st = dcrf_debug_selftest(self._h, which, nn, sd, &bad)
+        _check(st)
+        return int(bad)
 
     def _set_iteration_mode(self, int mode):
         _check(dcrf_set_iteration_mode(self._h, mode))

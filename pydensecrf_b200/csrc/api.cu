@@ -1135,6 +1135,23 @@ dcrf_status dcrf_flush_l2(dcrf_t* m) {
   });
 }
 
+dcrf_status dcrf_debug_selftest(dcrf_t* m, int which, uint64_t n, uint64_t seed, uint64_t* mismatches) {
+  return guarded([&] {
+    DCRF_REQUIRE(m && mismatches && (which == 0 || which == 1), "bad argument");
+    DeviceGuard g(m->device);
+    Ctx cx = m->cx();
+    unsigned long long* bad = dev_alloc<unsigned long long>(1, m->stream);
+    DCRF_CUDA(cudaMemsetAsync(bad, 0, sizeof(unsigned long long), m->stream));
+    launch_selftest(cx, which, n, seed, bad);
+    DCRF_CUDA(cudaGetLastError());
+    unsigned long long h = 0;
+    DCRF_CUDA(cudaMemcpyAsync(&h, bad, sizeof(h), cudaMemcpyDeviceToHost, m->stream));
+    DCRF_CUDA(cudaStreamSynchronize(m->stream));
+    dev_free(bad, m->stream);
+    *mismatches = h;
+  });
+}
+
 // ---- introspection -----------------------------------------------------------------------------------
 int dcrf_num_pairwise(const dcrf_t* m) { return m ? (int)m->terms.size() : 0; }
 dcrf_status dcrf_lattice_info(const dcrf_t* m, int k, int* d, int* N, int* V) {

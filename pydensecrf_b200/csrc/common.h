@@ -204,8 +204,11 @@ struct FusedArgs {
   const float* U;  // may be null (no unary)
   int neg_unary;   // 1: start from -U (inference), 0: start from 0-U (stepInference)
   float* Q;
+  float c_one, c_nzero, c_mone;  // 1, -0, -1: filled in by launch_fused_update (opaque operands of the packed kernel)
   FusedTerm t[kMaxFusedTerms];
 };
+// arithmetic self-tests (see k_selftest); *bad (device) receives the number of mismatching elements
+void launch_selftest(Ctx cx, int which, unsigned long long n, unsigned long long seed, unsigned long long* bad);
 bool fused_update_supported(RowLayout rl);
 // Q = softmax_col( -U - sum_k compat_k(norm_k * slice_k) ), everything in one pass
 void launch_fused_update(Ctx cx, RowLayout rl, const FusedArgs& a, bool fast);

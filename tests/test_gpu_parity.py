@@ -606,3 +606,11 @@ def test_1080p_properties(dcrf):
     for k, (dd, frac_lo, frac_hi) in enumerate([(2, 0.05, 0.3), (5, 0.05, 1.5)]):
         d_, N_, V_ = d._lattice_info(k)
         assert d_ == dd and N_ == W * H and frac_lo * N_ < V_ < frac_hi * N_
+
+
+def test_restated_arithmetic_selftests(dcrf):
+    """The packed (FFMA2) restatement of Eigen's pexp equals the scalar restatement for every float in [-100, 0],
+    and the shared-reciprocal column division equals IEEE division on 4e9 random operand pairs."""
+    d = dcrf.DenseCRF(4, 3)
+    assert d._selftest(0) == 0
+    assert d._selftest(1, n=4_000_000_000, seed=12345) == 0
