@@ -1,4 +1,5 @@
-"""Timings of the other BASELINE configs (cfg 3, 4, 5) at full size on one B200; prints one line each."""
+"""Timings of the other BASELINE configs (cfg 3, 4, 5, and cfg 2 on the i.i.d.-noise worst-case image) at full size on
+one B200; prints one line each."""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -8,10 +9,27 @@ import pydensecrf_b200.eigen as eigen
 from pydensecrf_b200 import utils
 from tests import workloads as wl
 
-which = sys.argv[1:] or ["cfg4", "cfg5", "cfg3"]
+which = sys.argv[1:] or ["cfg2noise", "cfg4", "cfg5", "cfg3"]
 
 def tm(f):
     t = time.perf_counter(); r = f(); return r, (time.perf_counter() - t) * 1e3
+
+if "cfg2noise" in which:
+    # the i.i.d.-uniform image is the worst case for the bilateral lattice (every pixel its own colour cell)
+    W, H, L = 1920, 1080, 21
+    d = dcrf.DenseCRF2D(W, H, L)
+    d.setUnaryEnergy(wl.softmax_unary(H, W, L, seed=0))
+    _, ta = tm(lambda: (d.addPairwiseGaussian(3, 3), d.addPairwiseBilateral(80, 13, wl.noise_image(H, W, seed=0), 10), d.synchronize()))
+    Q = eigen.MatrixXf()
+    for _ in range(3): d.inferenceInto(10, Q)
+    d._timer_start()
+    for _ in range(5): d.inferenceInto(10, Q)
+    ms = d._timer_stop() / 5
+    lat = [d._lattice_info(k)[::2] for k in range(2)]
+    b = wl.stage_bytes_per_iter(W * H, L, lat) * 10
+    print("cfg2 on the noise image (worst case): lattices %.0f ms (V=%s), inference(10) %.2f ms -> %.0f MPix*iter/s; stage model %.2f GB -> %.2f TB/s"
+          % (ta, [v for _, v in lat], ms, W * H * 10 / ms / 1e3, b / 1e9, b / ms / 1e9))
+    del d, Q
 
 if "cfg4" in which:
     W = H = 512; L = 21; n_img = 24
