@@ -250,6 +250,16 @@ def run_b200(args):
         barrier(dist, torch)
         return max_over_ranks(t_ms, dist, torch, local) / args.steps, out_h
 
+    # PCIe rates seen by this process on this box (they differ from box to box and bound the end-to-end step)
+    def _ms(f, reps=3):
+        f()
+        t_0 = time.perf_counter()
+        for _ in range(reps):
+            f()
+        return (time.perf_counter() - t_0) / reps * 1e3
+
+    h2d_ms = _ms(lambda: (d.setUnaryEnergy(Up), d.synchronize()))
+    d2h_ms = _ms(lambda: np.asarray(d.inference(0)))   # inference(0) = one softmax launch (0.13 ms) + the download of Q
     e_ms, Qh = e2e_loop(Up, np.asarray)
     e_ms_pageable, _ = e2e_loop(U, np.asarray)
     e_ms_map, Mh = e2e_loop(Up, d.currentMap)
@@ -257,6 +267,8 @@ def run_b200(args):
            "h2d_bytes_per_step": int(U.nbytes), "d2h_bytes_per_step": int(Qh.nbytes),
            "api": "setUnaryEnergy(U_pinned) + np.asarray(inference(10)) per step: full Q (L*N floats) back to the host",
            "pageable_input_ms_per_step": e_ms_pageable,
+           "pcie": {"h2d_ms": h2d_ms, "h2d_gbs": U.nbytes / h2d_ms / 1e6, "d2h_ms": d2h_ms, "d2h_gbs": U.nbytes / d2h_ms / 1e6,
+                    "note": "page-locked transfers of one step's input / result as measured in this run"},
            "map_output": {"ms_per_step": e_ms_map, "value": world * N * N_ITER / (e_ms_map * 1e-3) / 1e6,
                           "d2h_bytes_per_step": int(Mh.nbytes),
                           "api": "same, but currentMap(Q): the int16 label map comes back instead of Q"}}
@@ -277,6 +289,7 @@ def run_b200(args):
     for b in inputs[1:]:
         b[...] = U
     start = threading.Barrier(n_thr + 1)
+    compute_lane = threading.Lock()
     sums = [0.0] * n_thr
 
     def pipe_worker(k):
@@ -286,8 +299,11 @@ def run_b200(args):
             np.asarray(m.inference(N_ITER))
         start.wait()
         for _ in range(args.steps):
-            m.setUnaryEnergy(uh)
-            q = np.asarray(m.inference(N_ITER))
+            m.setUnaryEnergy(uh)           # H2D on the model's stream; returns once enqueued
+            with compute_lane:             # one inference on the SMs at a time (two would evict each other's L2 lines)
+                Qd = m.inference(N_ITER)
+                m.synchronize()
+            q = np.asarray(Qd)             # D2H, overlaps the next thread's inference
         sums[k] = float(q[0, 0])
 
     threads = [threading.Thread(target=pipe_worker, args=(k,)) for k in range(n_thr)]
@@ -305,7 +321,8 @@ def run_b200(args):
         e2e["pipelined"] = {"host_threads": n_thr, "ms_per_step": p_ms,
                             "value": world * N * N_ITER / (p_ms * 1e-3) / 1e6,
                             "note": "same per-step API calls and bytes as e2e.value, issued from %d host threads with one "
-                                    "model (own stream) each so that copies overlap kernels; throughput, not latency" % n_thr}
+                                    "model (own stream) each and a lock around inference, so that the copies of one step "
+                                    "overlap the kernels of another; throughput, not latency" % n_thr}
     del models[1:], inputs[1:]
 
     # ---- per-kernel durations: same steps, every launch bracketed by CUDA events ---------------------

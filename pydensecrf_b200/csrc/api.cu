@@ -404,6 +404,7 @@ void mf_step(dcrf_model* m, float* Q, bool neg_unary) {
     DCRF_REQUIRE(can_fuse(m), "fused iteration not available for this model (matrix compatibility, >128 labels or >8 terms)");
     FusedArgs a;
     a.N = m->N;
+    a.W = m->W, a.H = m->H;
     a.nterms = (int)m->terms.size();
     a.U = m->U;
     a.neg_unary = neg_unary ? 1 : 0;
@@ -458,7 +459,7 @@ void mf_init(dcrf_model* m, float* Q) {
   Ctx cx = m->cx();
   if (m->iter_mode != 1 && fused_update_supported(m->rl) && (uint64_t)m->N * m->rl.Lp < (1ull << 31)) {
     FusedArgs a;
-    a.N = m->N, a.nterms = 0, a.U = m->U, a.neg_unary = 1, a.Q = Q;
+    a.N = m->N, a.W = m->W, a.H = m->H, a.nterms = 0, a.U = m->U, a.neg_unary = 1, a.Q = Q;
     launch_fused_update(cx, m->rl, a, m->fast_softmax);
   } else {
     ensure_scratch(m);

@@ -201,6 +201,7 @@ struct FusedTerm {
 };
 struct FusedArgs {
   int N, nterms;
+  int W = 0, H = 0;  // image size of a 2-D model (pixel i = y*W + x), 0 = unknown: lets the update kernel walk 2-D tiles
   const float* U;  // may be null (no unary)
   int neg_unary;   // 1: start from -U (inference), 0: start from 0-U (stepInference)
   float* Q;
