@@ -197,6 +197,7 @@ struct Term {
   float* Wm = nullptr;    // L*L floats, symmetrised
   float *Whi = nullptr, *Wlo = nullptr;  // tf32 split of Wm, zero padded (tensor-core path)
   float *valA = nullptr, *valB = nullptr;  // (V+1) x Lp ping-pong value buffers (one allocation)
+  float* msg = nullptr;                    // N x Lp message of this term (tensor-core update path only)
   size_t val_bytes = 0;
   bool pre() const { return ntype == DCRF_NORMALIZE_SYMMETRIC || ntype == DCRF_NORMALIZE_BEFORE; }
   bool post() const { return ntype == DCRF_NORMALIZE_SYMMETRIC || ntype == DCRF_NORMALIZE_AFTER; }
@@ -296,7 +297,7 @@ dcrf_model* model_new(int N, int L, int W, int H, int device) {
 void term_free(dcrf_model* m, Term* t) {
   cudaStream_t s = m->stream;
   t->lat.release(s);
-  for (void* p : {(void*)t->norm, (void*)t->diag, (void*)t->Wm, (void*)t->Whi, (void*)t->Wlo, (void*)t->valA})
+  for (void* p : {(void*)t->norm, (void*)t->diag, (void*)t->Wm, (void*)t->Whi, (void*)t->Wlo, (void*)t->valA, (void*)t->msg})
     dev_free(p, s);
   delete t;
 }
@@ -309,6 +310,9 @@ void ensure_val(dcrf_model* m, Term* t) {
   // row 0 (absent neighbour) must read as zero forever; the kernels never write it
   DCRF_CUDA(cudaMemsetAsync(t->valA, 0, 2 * n * sizeof(float), m->stream));
   t->val_bytes = 2 * n * sizeof(float);
+}
+void ensure_msg(dcrf_model* m, Term* t) {
+  if (!t->msg) t->msg = dev_alloc<float>((size_t)m->N * m->rl.Lp, m->stream);
 }
 void ensure_scratch(dcrf_model* m) {
   const size_t n = (size_t)m->N * m->rl.Lp;
@@ -346,6 +350,13 @@ const float* run_filter(Ctx cx, const Lattice& lt, RowLayout rl, const float* in
   return src;
 }
 
+// Tensor cores for a MatrixCompatibility term?  Mode 2: always; mode 0: from 64 labels up and only for normalised
+// kernels (un-normalised messages are large enough for the 3xTF32 products to cost ~7e-5 on Q at 250 labels).
+bool tc_wanted(const dcrf_model* m, const Term* t) {
+  if (m->matrix_mode == 2) return true;
+  return m->matrix_mode == 0 && m->L >= 64 && t->ntype != DCRF_NO_NORMALIZATION;
+}
+
 bool can_fuse(dcrf_model* m) {
   if (!fused_update_supported(m->rl) || (int)m->terms.size() > kMaxFusedTerms) return false;
   if ((uint64_t)m->N * m->rl.Lp >= (1ull << 31)) return false;  // the fused kernel indexes rows with 32 bits
@@ -374,7 +385,7 @@ void term_apply(dcrf_model* m, Term* t, const float* Q, int mode, bool neg_unary
     ensure_scratch(m);
     DCRF_REQUIRE(out != m->msg, "internal: matrix term needs msg as scratch");
     launch_slice(cx, t->lat, m->rl, fin, t->post() ? t->norm : nullptr, nullptr, SLICE_WRITE, nullptr, false, m->msg);
-    const bool tc = t->Whi && (m->matrix_mode == 2 || (m->matrix_mode == 0 && m->L >= 64));
+    const bool tc = t->Whi && tc_wanted(m, t);
     if (tc)
       launch_matrix_compat_tc(cx, m->rl, m->N, t->Whi, t->Wlo, m->msg, mode, m->U, neg_unary, out);
     else
@@ -396,10 +407,52 @@ void ensure_aux(dcrf_model* m, int nterms) {
   if (!m->fork) DCRF_CUDA(cudaEventCreateWithFlags(&m->fork, cudaEventDisableTiming));
 }
 
+// every term's filter (splat + blurs) for the current Q; term k > 0 runs on its own side stream next to term 0 and
+// joins the main stream again before returning.  vals[k] = the buffer holding term k's blurred vertex values.
+// slice_msgs: also slice + post-normalise each term into its own message array (Term::msg) on the same stream.
+void filter_all_terms(dcrf_model* m, const float* Q, const float** vals, bool slice_msgs = false) {
+  Ctx cx = m->cx();
+  const int nterms = (int)m->terms.size();
+  for (int k = 0; k < nterms; k++) ensure_val(m, m->terms[k]);
+  // per-launch profiling wants clean, serialised durations: no overlap while it is on
+  const bool overlap = m->overlap_terms && nterms > 1 && !m->prof.enabled;
+  if (overlap) {
+    ensure_aux(m, nterms);
+    DCRF_CUDA(cudaEventRecord(m->fork, m->stream));
+  }
+  for (int k = 0; k < nterms; k++) {
+    Term* t = m->terms[k];
+    Ctx ck = cx;
+    if (overlap && k > 0) {
+      ck.stream = m->aux[k - 1];
+      DCRF_CUDA(cudaStreamWaitEvent(ck.stream, m->fork, 0));
+    }
+    vals[k] = run_filter(ck, t->lat, m->rl, Q, t->pre() ? t->norm : nullptr, t->valA, t->valB);
+    if (slice_msgs) {
+      ensure_msg(m, t);
+      launch_slice(ck, t->lat, m->rl, vals[k], t->post() ? t->norm : nullptr, nullptr, SLICE_WRITE, nullptr, false, t->msg);
+    }
+    if (overlap && k > 0) {
+      DCRF_CUDA(cudaEventRecord(m->aux_done[k - 1], ck.stream));
+      DCRF_CUDA(cudaStreamWaitEvent(m->stream, m->aux_done[k - 1], 0));
+    }
+  }
+}
+
+// all terms MatrixCompatibility on the tensor-core path: one kernel does every term's GEMM, the unary and the softmax
+// (matrix_tc.cu: k_update_matrix_tc)
+bool can_tc_update(dcrf_model* m) {
+  if (m->iter_mode == 1 || m->terms.empty()) return false;
+  for (Term* t : m->terms)
+    if (t->ckind != DCRF_COMPAT_MATRIX || !t->Whi || !tc_wanted(m, t)) return false;
+  return update_matrix_tc_supported(m->rl, (int)m->terms.size());
+}
+
 // one mean-field update of Q in place (the loop body of densecrf.cpp:122-129 / :187-200)
 void mf_step(dcrf_model* m, float* Q, bool neg_unary) {
   Ctx cx = m->cx();
   const bool fuse = m->iter_mode == 2 || (m->iter_mode == 0 && can_fuse(m));
+  const float* vals[std::max(kMaxFusedTerms, kMaxTCUTerms)];
   if (fuse) {
     DCRF_REQUIRE(can_fuse(m), "fused iteration not available for this model (matrix compatibility, >128 labels or >8 terms)");
     FusedArgs a;
@@ -409,26 +462,11 @@ void mf_step(dcrf_model* m, float* Q, bool neg_unary) {
     a.U = m->U;
     a.neg_unary = neg_unary ? 1 : 0;
     a.Q = Q;
-    for (int k = 0; k < a.nterms; k++) ensure_val(m, m->terms[k]);
-    // per-launch profiling wants clean, serialised durations: no overlap while it is on
-    const bool overlap = m->overlap_terms && a.nterms > 1 && !m->prof.enabled;
-    if (overlap) {
-      ensure_aux(m, a.nterms);
-      DCRF_CUDA(cudaEventRecord(m->fork, m->stream));
-    }
+    filter_all_terms(m, Q, vals);
     for (int k = 0; k < a.nterms; k++) {
       Term* t = m->terms[k];
       FusedTerm& ft = a.t[k];
-      Ctx ck = cx;
-      if (overlap && k > 0) {
-        ck.stream = m->aux[k - 1];
-        DCRF_CUDA(cudaStreamWaitEvent(ck.stream, m->fork, 0));
-      }
-      ft.val = run_filter(ck, t->lat, m->rl, Q, t->pre() ? t->norm : nullptr, t->valA, t->valB);
-      if (overlap && k > 0) {
-        DCRF_CUDA(cudaEventRecord(m->aux_done[k - 1], ck.stream));
-        DCRF_CUDA(cudaStreamWaitEvent(m->stream, m->aux_done[k - 1], 0));
-      }
+      ft.val = vals[k];
       ft.pix = t->lat.pix;
       ft.post_norm = t->post() ? t->norm : nullptr;
       ft.diag = t->diag;
@@ -438,6 +476,20 @@ void mf_step(dcrf_model* m, float* Q, bool neg_unary) {
       ft.ckind = t->ckind;
     }
     launch_fused_update(cx, m->rl, a, m->fast_softmax);
+  } else if (can_tc_update(m)) {
+    TCUArgs a;
+    a.N = m->N;
+    a.nterms = (int)m->terms.size();
+    a.U = m->U;
+    a.neg_unary = neg_unary ? 1 : 0;
+    a.Q = Q;
+    filter_all_terms(m, Q, vals, true);
+    for (int k = 0; k < a.nterms; k++) {
+      Term* t = m->terms[k];
+      a.t[k].msg = t->msg;
+      a.t[k].Bhi = t->Whi, a.t[k].Blo = t->Wlo;
+    }
+    launch_update_matrix_tc(cx, m->rl, a);
   } else {
     ensure_scratch(m);
     if (m->terms.empty()) launch_init_acc(cx, m->rl, m->N, m->U, neg_unary, m->acc);
@@ -448,6 +500,12 @@ void mf_step(dcrf_model* m, float* Q, bool neg_unary) {
 }
 
 void ensure_scratch_if_staged(dcrf_model* m) {
+  const bool init_fused = m->iter_mode != 1 && fused_update_supported(m->rl) && (uint64_t)m->N * m->rl.Lp < (1ull << 31);
+  if (can_tc_update(m)) {  // per-term messages; the accumulator pair only for a staged initial softmax
+    for (Term* t : m->terms) ensure_msg(m, t);
+    if (!init_fused) ensure_scratch(m);
+    return;
+  }
   const bool fuse = m->iter_mode == 2 || (m->iter_mode == 0 && can_fuse(m));
   if (!fuse || !(m->iter_mode != 1 && fused_update_supported(m->rl) && (uint64_t)m->N * m->rl.Lp < (1ull << 31))) ensure_scratch(m);
   for (Term* t : m->terms)

@@ -221,6 +221,23 @@ void launch_init_acc(Ctx cx, RowLayout rl, int N, const float* U, bool neg_unary
 void launch_matrix_compat(Ctx cx, RowLayout rl, int N, const float* W, const float* msg, int mode, const float* U,
                           bool neg_unary, float* out);
 
+// compatibility GEMMs of all terms + unary + softmax in one tensor-core kernel when every term has a
+// MatrixCompatibility (matrix_tc.cu)
+static const int kMaxTCUTerms = 4;
+struct TCUTerm {
+  const float* msg;  // N x Lp: the term's normalised slice (PairwisePotential::apply before the compatibility)
+  const float* Bhi;  // Np x Kp: tf32(W)
+  const float* Blo;  // Np x Kp: W - tf32(W)
+};
+struct TCUArgs {
+  int N, L, Lp, Np, Kp, neg_unary, nterms;
+  const float* U;  // may be null
+  float* Q;
+  TCUTerm t[kMaxTCUTerms];
+};
+bool update_matrix_tc_supported(RowLayout rl, int nterms);
+void launch_update_matrix_tc(Ctx cx, RowLayout rl, TCUArgs a);
+
 // tensor-core (tcgen05, 3xTF32) MatrixCompatibility (matrix_tc.cu)
 bool matrix_tc_supported(RowLayout rl);
 void matrix_tc_dims(RowLayout rl, int* Np, int* Kp);
