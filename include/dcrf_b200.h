@@ -118,6 +118,19 @@ dcrf_status dcrf_kl_divergence(dcrf_t* m, dcrf_mat_t* Q, double* out);
  * per-pixel argmax of Q computed on the device, first maximum wins; labels_N receives N int16. */
 dcrf_status dcrf_current_map(dcrf_t* m, dcrf_mat_t* Q, int16_t* labels_N);
 
+/* a batch of independent images of one size with shared kernel parameters (BASELINE cfg 4).  For every
+ * image b the call does what a caller of the reference does per image --
+ *   d = DenseCRF2D(W, H, L); d.setUnaryEnergy(unary[b]); d.addPairwiseGaussian((g_sx, g_sy), g_w);
+ *   d.addPairwiseBilateral((b_sx, b_sy), (b_sr, b_sg, b_sb), rgb[b], b_w); Q = d.inference(n_iterations); MAP = argmax(Q)
+ * (examples/inference.py:69-122; Potts compatibilities, NORMALIZE_SYMMETRIC) -- from n_workers host threads (0 = 4), each
+ * with its own model and stream, so that lattice construction, uploads and kernels of different images overlap on the
+ * device.  Results are identical to the per-image calls.  labels[b] receives N int16; q_out (may be NULL) points to B
+ * arrays of L*N floats that receive Q in the (L, N) row-major layout of np.array(Q). */
+dcrf_status dcrf_batch_map_2d(int W, int H, int L, int device, int B, const float* const* unary_LxN,
+                              const uint8_t* const* rgb_HxWx3, float g_sx, float g_sy, float g_w, float b_sx, float b_sy,
+                              float b_sr, float b_sg, float b_sb, float b_w, int n_iterations, int n_workers,
+                              int16_t* const* labels, float* const* q_out);
+
 /* ---- matrices: the eigen.MatrixXf / eigen.VectorXf objects of the reference -------------------- */
 /* replaces eigen.MatrixXf() (empty 0x0)               pydensecrf/eigen.pyx:62-66 */
 dcrf_status dcrf_mat_create_empty(dcrf_mat_t** out);

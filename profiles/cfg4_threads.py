@@ -34,3 +34,14 @@ for nt in (1, 2, 4, 8):
     t0 = time.perf_counter(); [t.start() for t in ths]; [t.join() for t in ths]; dt = time.perf_counter() - t0
     print("cfg4 one GPU, %d host thread(s): %.0f images/s (%.2f ms per image, %.0f MPix*iter/s incl. lattice builds and transfers)"
           % (nt, n_img / dt, dt / n_img * 1e3, n_img * W * H * 5 / dt / 1e6))
+
+# the same through the library's batch entry (worker threads inside the C++ core, one call from Python)
+Bn = 256
+Ub = pinned_empty((Bn, L, W * H)); Ib = np.empty((Bn, H, W, 3), np.uint8)
+for b in range(Bn):
+    Ub[b] = Us[b % 4]; Ib[b] = imgs[b % 4]
+for nw in (1, 4, 8):
+    dcrf.map_batch_2d(Ub[:16], Ib[:16], n_iter=5, workers=nw)
+    t0 = time.perf_counter(); lab = dcrf.map_batch_2d(Ub, Ib, n_iter=5, workers=nw); dt = time.perf_counter() - t0
+    assert np.array_equal(lab[1].ravel(), ref)
+    print("cfg4 one GPU, map_batch_2d(workers=%d): %.0f images/s (%.2f ms per image)" % (nw, Bn / dt, dt / Bn * 1e3))

@@ -12,6 +12,7 @@ import enum
 
 from cpython.buffer cimport PyBUF_WRITABLE
 from libc.stdint cimport int16_t, int32_t, int64_t, uint8_t, uint64_t
+from libc.stdlib cimport malloc, free
 
 
 cdef extern from "dcrf_b200.h" nogil:
@@ -62,6 +63,9 @@ cdef extern from "dcrf_b200.h" nogil:
     int64_t dcrf_launch_count(const dcrf_t* m)
     int dcrf_flush_l2(dcrf_t* m)
     int dcrf_debug_selftest(dcrf_t* m, int which, uint64_t n, uint64_t seed, uint64_t* mismatches)
+    int dcrf_batch_map_2d(int W, int H, int L, int device, int B, const float* const* unary, const uint8_t* const* rgb,
+                          float g_sx, float g_sy, float g_w, float b_sx, float b_sy, float b_sr, float b_sg, float b_sb,
+                          float b_w, int n_iterations, int n_workers, int16_t* const* labels, float* const* q_out)
     int dcrf_num_pairwise(const dcrf_t* m)
     int dcrf_lattice_info(const dcrf_t* m, int k, int* d, int* N, int* V)
     int dcrf_lattice_dump(dcrf_t* m, int k, int32_t* offset, float* bary, int16_t* keys, int32_t* nbr, float* norm)
@@ -365,6 +369,66 @@ cdef class LogisticUnary(Unary):
         self._u = L.copy()
         self._f = f.copy()
         self._logistic = True
+
+
+def map_batch_2d(float[:, :, ::1] unaries not None, unsigned char[:, :, :, ::1] images not None, sxy_gaussian=3,
+                 compat_gaussian=3, sxy_bilateral=80, srgb=13, compat_bilateral=10, int n_iter=5, int workers=4,
+                 device=None, bint return_q=False):
+    """MAP labelling of a batch of images of one size with shared kernel parameters (SURVEY 8f-3, BASELINE cfg 4).
+
+    unaries: (B, nlabels, H*W) float32, images: (B, H, W, 3) uint8.  Per image this is DenseCRF2D(W, H, nlabels) +
+    setUnaryEnergy + addPairwiseGaussian(sxy_gaussian, compat_gaussian) + addPairwiseBilateral(sxy_bilateral, srgb,
+    image, compat_bilateral) + inference(n_iter) + argmax, with identical results, but the images are spread over
+    `workers` host threads inside the library (each with its own model and CUDA stream), so that lattice construction,
+    uploads and kernels of different images overlap.  Returns (B, H, W) int16 labels, and Q (B, nlabels, H*W) float32 as
+    well if return_q.  Inputs in page-locked memory (utils.pinned_empty) upload about five times faster."""
+    import numpy as np
+    cdef int B = <int>unaries.shape[0], L = <int>unaries.shape[1]
+    cdef int H = <int>images.shape[1], W = <int>images.shape[2]
+    if images.shape[0] != B:
+        raise ValueError("unaries and images disagree on the batch size ({} vs {})".format(B, images.shape[0]))
+    if images.shape[3] != 3:
+        raise ValueError("images must be (B, H, W, 3) uint8")
+    if unaries.shape[2] != H * W:
+        raise ValueError("Bad shape for unary energy (Need {}, got {})".format((B, L, H * W), tuple(unaries.shape)))
+    if isinstance(sxy_gaussian, Number):
+        sxy_gaussian = (sxy_gaussian, sxy_gaussian)
+    if isinstance(sxy_bilateral, Number):
+        sxy_bilateral = (sxy_bilateral, sxy_bilateral)
+    if isinstance(srgb, Number):
+        srgb = (srgb, srgb, srgb)
+    if not isinstance(compat_gaussian, Number) or not isinstance(compat_bilateral, Number):
+        raise ValueError("map_batch_2d takes Potts compatibilities (numbers)")
+    labels = np.empty((B, H, W), dtype=np.int16)
+    q = np.empty((B, L, H * W), dtype=np.float32) if return_q else None
+    cdef int16_t[:, :, ::1] lab_v = labels
+    cdef float[:, :, ::1] q_v = q
+    cdef const float** up = <const float**>malloc(max(B, 1) * sizeof(void*))
+    cdef const uint8_t** ip = <const uint8_t**>malloc(max(B, 1) * sizeof(void*))
+    cdef int16_t** lp = <int16_t**>malloc(max(B, 1) * sizeof(void*))
+    cdef float** qp = <float**>malloc(max(B, 1) * sizeof(void*))
+    cdef int b, st
+    cdef int dev = -1 if device is None else int(device)
+    cdef float gsx = sxy_gaussian[0], gsy = sxy_gaussian[1], gw = compat_gaussian
+    cdef float bsx = sxy_bilateral[0], bsy = sxy_bilateral[1], sr = srgb[0], sg = srgb[1], sb = srgb[2], bw = compat_bilateral
+    try:
+        if up == NULL or ip == NULL or lp == NULL or qp == NULL:
+            raise MemoryError()
+        for b in range(B):
+            up[b] = &unaries[b, 0, 0]
+            ip[b] = &images[b, 0, 0, 0]
+            lp[b] = &lab_v[b, 0, 0]
+            qp[b] = &q_v[b, 0, 0] if return_q else NULL
+        with nogil:
+            st = dcrf_batch_map_2d(W, H, L, dev, B, up, ip, gsx, gsy, gw, bsx, bsy, sr, sg, sb, bw, n_iter, workers,
+                                   lp, qp if return_q else NULL)
+        _check(st)
+    finally:
+        free(up)
+        free(ip)
+        free(lp)
+        free(qp)
+    return (labels, q) if return_q else labels
 
 
 cdef int _device_arg(dict kw) except? -2:

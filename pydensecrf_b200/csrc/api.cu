@@ -12,7 +12,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <atomic>
 #include <mutex>
+#include <thread>
 
 #include "common.h"
 
@@ -1191,6 +1193,63 @@ dcrf_status dcrf_flush_l2(dcrf_t* m) {
     }
     m->prof.launches++;
     DCRF_CUDA(cudaMemsetAsync(m->flush_buf, 0x5a, m->flush_bytes, m->stream));
+  });
+}
+
+dcrf_status dcrf_batch_map_2d(int W, int H, int L, int device, int B, const float* const* unary_LxN,
+                              const uint8_t* const* rgb_HxWx3, float g_sx, float g_sy, float g_w, float b_sx, float b_sy,
+                              float b_sr, float b_sg, float b_sb, float b_w, int n_iterations, int n_workers,
+                              int16_t* const* labels, float* const* q_out) {
+  return guarded([&] {
+    DCRF_REQUIRE(W > 0 && H > 0 && L > 0 && B >= 0 && n_iterations >= 0, "bad batch shape");
+    DCRF_REQUIRE(B == 0 || (unary_LxN && rgb_HxWx3 && labels), "null argument");
+    const int nw = std::max(1, std::min(n_workers > 0 ? n_workers : 4, B));
+    std::atomic<int> next{0};
+    std::atomic<bool> failed{false};
+    std::mutex mu;
+    std::string first_error;
+    dcrf_status first_status = DCRF_OK;
+    auto worker = [&] {
+      const size_t N = (size_t)W * H;
+      for (;;) {
+        const int b = next.fetch_add(1);
+        if (b >= B || failed.load()) return;
+        dcrf_t* m = nullptr;
+        dcrf_mat_t* Q = nullptr;
+        dcrf_status st = dcrf_create_2d(W, H, L, device, &m);
+        if (st == DCRF_OK) st = dcrf_set_unary_const(m, unary_LxN[b]);
+        if (st == DCRF_OK) st = dcrf_add_pairwise_gaussian(m, g_sx, g_sy, DCRF_COMPAT_POTTS, &g_w, 1, DCRF_NORMALIZE_SYMMETRIC);
+        if (st == DCRF_OK)
+          st = dcrf_add_pairwise_bilateral(m, b_sx, b_sy, b_sr, b_sg, b_sb, rgb_HxWx3[b], DCRF_COMPAT_POTTS, &b_w, 1,
+                                           DCRF_NORMALIZE_SYMMETRIC);
+        if (st == DCRF_OK) st = dcrf_inference(m, n_iterations, &Q);
+        if (st == DCRF_OK) st = dcrf_current_map(m, Q, labels[b]);
+        if (st == DCRF_OK && q_out && q_out[b]) {
+          float* host = nullptr;  // Eigen layout: N columns of L floats -> (L, N) row-major for the caller
+          st = dcrf_mat_host_ptr(Q, &host);
+          if (st == DCRF_OK) {
+            float* dst = q_out[b];
+            for (size_t i = 0; i < N; i++)
+              for (int l = 0; l < L; l++) dst[(size_t)l * N + i] = host[i * L + l];
+            dcrf_mat_release_host(Q);
+          }
+        }
+        if (st != DCRF_OK) {
+          std::lock_guard<std::mutex> g(mu);
+          if (!failed.exchange(true)) {
+            first_status = st;
+            first_error = "image " + std::to_string(b) + ": " + dcrf_last_error();
+          }
+        }
+        if (Q) dcrf_mat_destroy(Q);
+        if (m) dcrf_destroy(m);
+      }
+    };
+    std::vector<std::thread> pool;
+    for (int k = 1; k < nw; k++) pool.emplace_back(worker);
+    worker();
+    for (auto& t : pool) t.join();
+    if (failed.load()) throw Error(first_status, first_error);
   });
 }
 

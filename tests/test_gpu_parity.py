@@ -656,3 +656,31 @@ def test_restated_arithmetic_selftests(dcrf):
     d = dcrf.DenseCRF(4, 3)
     assert d._selftest(0) == 0
     assert d._selftest(1, n=4_000_000_000, seed=12345) == 0
+
+
+def test_map_batch_2d_equals_per_image_calls(dcrf):
+    """the batch entry (worker threads inside the library, one model and stream each) returns exactly what
+    the per-image calls return, in the caller's order, for more images than workers; errors surface as ValueError."""
+    from tests import workloads as wl
+
+    W, H, L, B = 96, 64, 7, 9
+    U = np.stack([wl.softmax_unary(H, W, L, seed=b, grid=8) for b in range(B)])
+    I = np.stack([wl.smooth_image(H, W, seed=b, grid=8) for b in range(B)])
+    labels, Q = dcrf.map_batch_2d(U, I, sxy_gaussian=3, compat_gaussian=3, sxy_bilateral=(40, 30), srgb=(13, 11, 9),
+                                  compat_bilateral=10, n_iter=5, workers=4, return_q=True)
+    assert labels.shape == (B, H, W) and labels.dtype == np.int16 and Q.shape == (B, L, H * W)
+    for b in range(B):
+        d = dcrf.DenseCRF2D(W, H, L)
+        d.setUnaryEnergy(U[b])
+        d.addPairwiseGaussian(sxy=3, compat=3)
+        d.addPairwiseBilateral(sxy=(40, 30), srgb=(13, 11, 9), rgbim=I[b], compat=10)
+        Qb = d.inference(5)
+        assert np.array_equal(Q[b], np.array(Qb))
+        assert np.array_equal(labels[b].ravel(), d.currentMap(Qb))
+    only = dcrf.map_batch_2d(U[:2], I[:2], n_iter=2, workers=1)
+    assert only.shape == (2, H, W)
+    assert dcrf.map_batch_2d(U[:0], I[:0]).shape == (0, H, W)
+    with pytest.raises(ValueError):
+        dcrf.map_batch_2d(U[:, :, :-1].copy(), I)
+    with pytest.raises(ValueError):
+        dcrf.map_batch_2d(U, I[:3])
