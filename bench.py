@@ -237,9 +237,12 @@ def run_b200(args):
     Up[...] = U
 
     def e2e_loop(Uh, fetch):
-        for _ in range(2):
+        # warm-up with the timed loop's exact pattern: the previous result stays alive while the next one is computed,
+        # so two result matrices (device buffer, page-locked host mirror, CUDA graph each) exist before the clock starts
+        out_h = None
+        for _ in range(max(args.warmup, 3) + 1):
             d.setUnaryEnergy(Uh)
-            fetch(d.inference(N_ITER))
+            out_h = fetch(d.inference(N_ITER))
         barrier(dist, torch)
         t_0 = time.perf_counter()
         for _ in range(args.steps):
@@ -294,9 +297,12 @@ def run_b200(args):
 
     def pipe_worker(k):
         m, uh = models[k], inputs[k]
-        for _ in range(2):
+        q = Qd = None
+        for _ in range(4):                 # same pattern as the timed loop (two result matrices alive per model)
             m.setUnaryEnergy(uh)
-            np.asarray(m.inference(N_ITER))
+            Qd = m.inference(N_ITER)
+            m.synchronize()
+            q = np.asarray(Qd)
         start.wait()
         for _ in range(args.steps):
             m.setUnaryEnergy(uh)           # H2D on the model's stream; returns once enqueued

@@ -662,7 +662,10 @@ cdef class DenseCRF:
         return out
 
     def synchronize(self):
-        _check(dcrf_synchronize(self._h))
+        cdef int st
+        with nogil:  # other Python threads keep driving their own models while this one waits
+            st = dcrf_synchronize(self._h)
+        _check(st)
 
     def _timer_start(self):
         _check(dcrf_timer_start(self._h))
