@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <atomic>
 #include <mutex>
 #include <thread>
@@ -189,8 +190,26 @@ static void mat_free_dev(dcrf_mat* a) {
 }
 
 // ---- model -------------------------------------------------------------------------------------
-struct Term {
+// A lattice that depends on the geometry only (DenseCRF2D::addPairwiseGaussian: image size and sxy) is the same for
+// every image of a video or batch, so it is built once per process and shared, read-only, by all terms that ask for it,
+// together with norm_ = compute(1) before the NormalizationType transform.  The last user frees it.
+struct SharedLattice {
+  int device = 0;
   Lattice lat;
+  float* norm_raw = nullptr;  // [N]
+  ~SharedLattice() {
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(device);
+    lat.release(nullptr);  // every user has synchronised its stream before dropping its reference
+    dev_free(norm_raw, nullptr);
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+struct Term {
+  Lattice lat;                          // shallow copy of shared->lat when shared is set
+  std::shared_ptr<SharedLattice> shared;
   float* norm = nullptr;  // [N]
   int ntype = DCRF_NORMALIZE_SYMMETRIC;
   int ckind = DCRF_COMPAT_POTTS;
@@ -298,7 +317,7 @@ dcrf_model* model_new(int N, int L, int W, int H, int device) {
 
 void term_free(dcrf_model* m, Term* t) {
   cudaStream_t s = m->stream;
-  t->lat.release(s);
+  if (!t->shared) t->lat.release(s);
   for (void* p : {(void*)t->norm, (void*)t->diag, (void*)t->Wm, (void*)t->Whi, (void*)t->Wlo, (void*)t->valA, (void*)t->msg})
     dev_free(p, s);
   delete t;
@@ -601,6 +620,67 @@ float* upload_tmp(dcrf_model* m, const void* host, size_t bytes) {
   return (float*)d;
 }
 
+// norm_ = lattice_.compute(ones)  (pairwise.cpp:44): a 1-label pass, which takes the seqCompute arithmetic
+float* raw_norm(dcrf_model* m, const Lattice& lat) {
+  Ctx cx = m->cx();
+  cudaStream_t s = m->stream;
+  const int N = m->N;
+  RowLayout r1(1);
+  float* ones = dev_alloc<float>(N, s);
+  launch_fill(cx, ones, N, 1.0f);
+  float* A = dev_alloc<float>((size_t)lat.V + 1, s);
+  float* B = dev_alloc<float>((size_t)lat.V + 1, s);
+  DCRF_CUDA(cudaMemsetAsync(A, 0, ((size_t)lat.V + 1) * sizeof(float), s));
+  DCRF_CUDA(cudaMemsetAsync(B, 0, ((size_t)lat.V + 1) * sizeof(float), s));
+  const float* fin = run_filter(cx, lat, r1, ones, nullptr, A, B);
+  float* norm = dev_alloc<float>(N, s);
+  launch_slice(cx, lat, r1, fin, nullptr, nullptr, SLICE_WRITE, nullptr, false, norm);
+  dev_free(ones, s);
+  dev_free(A, s);
+  dev_free(B, s);
+  return norm;
+}
+
+struct GeoKey {
+  int device, W, H;
+  uint32_t sx, sy;
+  bool operator==(const GeoKey& o) const { return device == o.device && W == o.W && H == o.H && sx == o.sx && sy == o.sy; }
+};
+// most recent last, at most 4 entries; heap objects that are never destroyed, so that no CUDA call runs from a static
+// destructor at process exit (entries still referenced by live models stay alive through their shared_ptr anyway)
+static std::mutex& g_geo_mu = *new std::mutex();
+static std::vector<std::pair<GeoKey, std::shared_ptr<SharedLattice>>>& g_geo_cache =
+    *new std::vector<std::pair<GeoKey, std::shared_ptr<SharedLattice>>>();
+
+std::shared_ptr<SharedLattice> shared_gaussian_lattice(dcrf_model* m, const FeatureSource& src) {
+  static const bool off = [] {
+    const char* e = std::getenv("DCRF_B200_NO_LATTICE_CACHE");
+    return e && std::atoi(e) != 0;
+  }();
+  GeoKey key{m->device, m->W, m->H, 0, 0};
+  std::memcpy(&key.sx, &src.s[0], 4);
+  std::memcpy(&key.sy, &src.s[1], 4);
+  if (!off) {
+    std::lock_guard<std::mutex> g(g_geo_mu);
+    for (auto& e : g_geo_cache)
+      if (e.first == key) return e.second;
+  }
+  auto sp = std::make_shared<SharedLattice>();
+  sp->device = m->device;
+  lattice_build(m->cx(), src, 2, m->N, &sp->lat);
+  sp->norm_raw = raw_norm(m, sp->lat);
+  DCRF_CUDA(cudaGetLastError());
+  DCRF_CUDA(cudaStreamSynchronize(m->stream));  // complete before any other stream may read it
+  if (!off) {
+    std::lock_guard<std::mutex> g(g_geo_mu);
+    for (auto& e : g_geo_cache)
+      if (e.first == key) return e.second;  // another thread was faster: use its copy, ours dies with sp
+    if (g_geo_cache.size() >= 4) g_geo_cache.erase(g_geo_cache.begin());
+    g_geo_cache.emplace_back(key, sp);
+  }
+  return sp;
+}
+
 void add_term(dcrf_model* m, const FeatureSource& src, int d, int compat_kind, const float* compat, int ktype,
               int ntype) {
   DCRF_REQUIRE(ntype >= 0 && ntype <= 3, "bad NormalizationType");
@@ -610,7 +690,12 @@ void add_term(dcrf_model* m, const FeatureSource& src, int d, int compat_kind, c
   cudaStream_t s = m->stream;
   Term* t = new Term();
   try {
-    lattice_build(cx, src, d, m->N, &t->lat);
+    if (src.kind == FEAT_GAUSS2D) {
+      t->shared = shared_gaussian_lattice(m, src);
+      t->lat = t->shared->lat;  // pointers only; owned by the shared object
+    } else {
+      lattice_build(cx, src, d, m->N, &t->lat);
+    }
     t->ntype = ntype;
     t->ckind = compat_kind;
     const int L = m->L, Lp = m->rl.Lp;
@@ -637,18 +722,13 @@ void add_term(dcrf_model* m, const FeatureSource& src, int d, int compat_kind, c
       }
       DCRF_CUDA(cudaStreamSynchronize(s));
     }
-    // norm_ = lattice_.compute(ones)  (pairwise.cpp:44): a 1-label pass, which takes the seqCompute arithmetic
     const int N = m->N;
-    RowLayout r1(1);
-    float* ones = dev_alloc<float>(N, s);
-    launch_fill(cx, ones, N, 1.0f);
-    float* A = dev_alloc<float>((size_t)t->lat.V + 1, s);
-    float* B = dev_alloc<float>((size_t)t->lat.V + 1, s);
-    DCRF_CUDA(cudaMemsetAsync(A, 0, ((size_t)t->lat.V + 1) * sizeof(float), s));
-    DCRF_CUDA(cudaMemsetAsync(B, 0, ((size_t)t->lat.V + 1) * sizeof(float), s));
-    const float* fin = run_filter(cx, t->lat, r1, ones, nullptr, A, B);
-    t->norm = dev_alloc<float>(N, s);
-    launch_slice(cx, t->lat, r1, fin, nullptr, nullptr, SLICE_WRITE, nullptr, false, t->norm);
+    if (t->shared) {
+      t->norm = dev_alloc<float>(N, s);
+      DCRF_CUDA(cudaMemcpyAsync(t->norm, t->shared->norm_raw, (size_t)N * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    } else {
+      t->norm = raw_norm(m, t->lat);
+    }
     if (ntype == DCRF_NO_NORMALIZATION) {
       // mean_norm = N / sum(norm): the reference adds N floats one after the other in float
       // (pairwise.cpp:47-51); that rounding sequence is inherently serial, so it runs on the host once
@@ -662,9 +742,6 @@ void add_term(dcrf_model* m, const FeatureSource& src, int d, int compat_kind, c
     } else {
       launch_norm_transform(cx, N, t->norm, ntype == DCRF_NORMALIZE_SYMMETRIC);
     }
-    dev_free(ones, s);
-    dev_free(A, s);
-    dev_free(B, s);
     DCRF_CUDA(cudaGetLastError());
     DCRF_CUDA(cudaStreamSynchronize(s));
   } catch (...) {

@@ -684,3 +684,45 @@ def test_map_batch_2d_equals_per_image_calls(dcrf):
         dcrf.map_batch_2d(U[:, :, :-1].copy(), I)
     with pytest.raises(ValueError):
         dcrf.map_batch_2d(U, I[:3])
+
+
+def test_gaussian_lattice_is_shared_between_models(dcrf, po):
+    """addPairwiseGaussian depends on the geometry only, so models of one image size share one lattice (built once per
+    process).  Sharing must not change results (different normalisations, models destroyed in any order, a different
+    sxy gets its own lattice) and the shared lattice must still equal the reference's."""
+    from tests import workloads as wl
+
+    W, H, L = 53, 37, 5
+    U = wl.softmax_unary(H, W, L, seed=3, grid=8)
+    img = wl.smooth_image(H, W, seed=3, grid=8)
+    outs = []
+    models = []
+    for nt in (dcrf.NORMALIZE_SYMMETRIC, dcrf.NO_NORMALIZATION, dcrf.NORMALIZE_BEFORE, dcrf.NORMALIZE_SYMMETRIC):
+        d = dcrf.DenseCRF2D(W, H, L)
+        d.setUnaryEnergy(U)
+        d.addPairwiseGaussian(sxy=(3, 2), compat=3, normalization=nt)
+        d.addPairwiseBilateral(sxy=30, srgb=13, rgbim=img, compat=5)
+        o = po.CRF((W, H), L, "orc")
+        o.setUnaryEnergy(U)
+        o.addPairwiseGaussian((3, 2), 3, normalization=int(nt))
+        o.addPairwiseBilateral(30, 13, img, 5)
+        outs.append((np.array(d.inference(3)), o.inference(3)))
+        models.append(d)
+    for q, qo in outs:
+        assert np.abs(q - qo).max() <= Q_ATOL
+    assert np.array_equal(outs[0][0], outs[3][0])
+    # lattice of the shared term, read through two different models, equals the reference's
+    feats = np.zeros((2, H * W), np.float32)
+    feats[0] = (np.arange(H * W) % W) / 3.0
+    feats[1] = (np.arange(H * W) // W) / 2.0
+    ref_off, ref_bary = po.Lattice(feats, "orc").dump()[:2]
+    for d in (models[0], models[2]):
+        off, bary = d._lattice_dump(0)[:2]
+        assert np.array_equal(off, ref_off) and np.array_equal(bary, ref_bary)
+    del models[0], outs
+    e = dcrf.DenseCRF2D(W, H, L)
+    e.setUnaryEnergy(U)
+    e.addPairwiseGaussian(sxy=(3, 2), compat=3)
+    e.addPairwiseGaussian(sxy=(5, 5), compat=1)   # second geometry: its own lattice
+    assert e._lattice_info(0)[2] != e._lattice_info(1)[2]
+    assert np.isfinite(np.array(e.inference(2))).all()
