@@ -19,3 +19,10 @@ for rep in range(4):
           % (rep, (t1-t0)*1e3, (t2-t1)*1e3, (t3-t2)*1e3, (t4-t3)*1e3, (t5-t4)*1e3, (t5-t0)*1e3))
 d._profile_enable(True); d._profile_read(True)
 d2 = None
+# per-kernel-class durations of one more bilateral lattice build (events around every launch)
+d.addPairwiseBilateral(80, 13, img, 10); d.synchronize()
+p = d._profile_read(True); d._profile_enable(False)
+tot = sum(v[1] for v in p.values())
+print("bilateral lattice build, GPU time by launch class (ms): total %.3f" % tot)
+for k, v in sorted(p.items(), key=lambda kv: -kv[1][1]):
+    print("   %-22s x%-3d %.3f" % (k, v[0], v[1]))
