@@ -33,6 +33,31 @@ __global__ void __launch_bounds__(256) k_gather(const float* __restrict__ rows, 
   reinterpret_cast<float4*>(out + g * kRowFloats)[c] = acc;
 }
 
+// LANES lanes per row, the first `active` of them load 16 bytes each (row pitch in floats given): does it matter whether
+// a quarter-warp (8 lanes = one 128-byte L1 request) spans one row or pieces of two?
+template <int LANES>
+__global__ void __launch_bounds__(256) k_gather_lanes(const float* __restrict__ rows, const int* __restrict__ idx, size_t ngroups,
+                                                     int per_group, float* __restrict__ out, int pitch, int active) {
+  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t g = q / LANES;
+  const int c = (int)(q % LANES);
+  if (g >= ngroups) return;
+  const int* my = idx + g * per_group;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int t = 0; t + 4 <= per_group; t += 4) {
+    int r[4];
+    float4 x[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) r[u] = __ldg(my + t + u);
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+      x[u] = c < active ? __ldg(reinterpret_cast<const float4*>(rows + (size_t)r[u] * pitch) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < 4; u++) acc.x += x[u].x, acc.y += x[u].y, acc.z += x[u].z, acc.w += x[u].w;
+  }
+  if (c < active) reinterpret_cast<float4*>(out + g * 32)[c] = acc;
+}
+
 __global__ void __launch_bounds__(256) k_stream(const float4* __restrict__ p, size_t n, int reps, float* __restrict__ out) {
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -98,6 +123,31 @@ int main() {
     const double ms128 = time_ms(e0, e1) / 5;
     cudaFree(rows128);
     printf("   rows/s: 96-byte pitch %.1f G, 128-byte pitch %.1f G\n", ngroups * per_group / ms4 / 1e6, ngroups * per_group / ms128 / 1e6);
+    {
+      float* rows128b;
+      cudaMalloc(&rows128b, nrows * 32 * sizeof(float));
+      cudaMemset(rows128b, 0, nrows * 32 * sizeof(float));
+      float* out2;
+      cudaMalloc(&out2, ngroups * 32 * sizeof(float));
+      auto run = [&](const char* name, int lanes, const float* tab, int pitch, int active) {
+        const unsigned gr = (unsigned)((ngroups * lanes + 255) / 256);
+        for (int w = 0; w < 6; w++) {
+          if (w == 1) cudaEventRecord(e0);
+          if (lanes == 8) k_gather_lanes<8><<<gr, 256>>>(tab, idx, ngroups, per_group, out2, pitch, active);
+          else k_gather_lanes<4><<<gr, 256>>>(tab, idx, ngroups, per_group, out2, pitch, active);
+        }
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        const double ms = time_ms(e0, e1) / 5;
+        printf("   %-52s %.1f G rows/s\n", name, ngroups * per_group / ms / 1e6);
+      };
+      run("8 lanes per row, 6 active, 96-byte pitch", 8, rows, 24, 6);
+      run("8 lanes per row, 6 active, 128-byte pitch", 8, rows128b, 32, 6);
+      run("8 lanes per row, 8 active, 128-byte rows", 8, rows128b, 32, 8);
+      run("4 lanes per row, 4 active, 64-byte rows (pitch 64)", 4, rows128b, 16, 4);
+      cudaFree(rows128b);
+      cudaFree(out2);
+    }
     printf("buffer %6.0f MB: random 96-byte rows %.0f GB/s (4 in flight) %.0f GB/s (8 in flight); streamed %.0f GB/s   [%s]\n", mb,
            bytes / ms4 / 1e6, bytes / ms8 / 1e6, (double)n4 * 16.0 * reps / mss / 1e6, cudaGetErrorString(cudaGetLastError()));
     cudaFree(rows);
