@@ -614,9 +614,66 @@ void mat_written(dcrf_model* m, dcrf_mat* a) {
   }
 }
 
+// Host array -> temporary device buffer on the model's stream.  Page-locked memory (utils.pinned_empty,
+// dcrf_host_alloc) goes by DMA at PCIe rate (~53 GB/s).  Ordinary pageable memory -- what a numpy array is -- would
+// reach the device at ~10 GB/s through the driver's own staging copy, so large pageable uploads are staged here: a few
+// threads memcpy the next chunk into one of two page-locked buffers while the previous chunk is on the bus.
+static void parallel_memcpy(char* dst, const char* src, size_t n, int nthreads) {
+  if (nthreads <= 1 || n < (1u << 20)) {
+    std::memcpy(dst, src, n);
+    return;
+  }
+  const size_t per = ((n + nthreads - 1) / nthreads + 63) & ~(size_t)63;
+  std::vector<std::thread> th;
+  for (int k = 1; k < nthreads; k++) {
+    const size_t o = (size_t)k * per;
+    if (o < n) th.emplace_back([=] { std::memcpy(dst + o, src + o, std::min(per, n - o)); });
+  }
+  std::memcpy(dst, src, std::min(per, n));
+  for (auto& t : th) t.join();
+}
+
 float* upload_tmp(dcrf_model* m, const void* host, size_t bytes) {
   char* d = dev_alloc<char>(bytes, m->stream);
-  DCRF_CUDA(cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, m->stream));
+  static const int nthreads = [] {
+    const char* e = std::getenv("DCRF_B200_UPLOAD_THREADS");
+    return e ? std::max(0, std::atoi(e)) : 4;
+  }();
+  cudaPointerAttributes at{};
+  const bool pageable = cudaPointerGetAttributes(&at, host) != cudaSuccess || at.type == cudaMemoryTypeUnregistered;
+  cudaGetLastError();
+  if (!pageable || nthreads == 0 || bytes < (16u << 20)) {  // below ~16 MB the thread start-up costs more than it saves
+    DCRF_CUDA(cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, m->stream));
+    return (float*)d;
+  }
+  const size_t mb = 1u << 20;
+  const size_t chunk = std::min((size_t)32 * mb, std::max((size_t)4 * mb, ((bytes / 4 + mb - 1) / mb) * mb));
+  char* stage[2] = {(char*)g_pinned.get(chunk), (char*)g_pinned.get(chunk)};
+  cudaEvent_t done[2] = {nullptr, nullptr};
+  try {
+    for (int k = 0; k < 2; k++) DCRF_CUDA(cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming));
+    int i = 0;
+    for (size_t off = 0; off < bytes; off += chunk, i++) {
+      const size_t n = std::min(chunk, bytes - off);
+      if (i >= 2) DCRF_CUDA(cudaEventSynchronize(done[i & 1]));  // the DMA that last read this staging buffer
+      parallel_memcpy(stage[i & 1], (const char*)host + off, n, nthreads);
+      DCRF_CUDA(cudaMemcpyAsync(d + off, stage[i & 1], n, cudaMemcpyHostToDevice, m->stream));
+      DCRF_CUDA(cudaEventRecord(done[i & 1], m->stream));
+    }
+    for (int k = 0; k < 2; k++) DCRF_CUDA(cudaEventSynchronize(done[k]));
+  } catch (...) {
+    cudaStreamSynchronize(m->stream);
+    for (int k = 0; k < 2; k++) {
+      if (done[k]) cudaEventDestroy(done[k]);
+      g_pinned.put(stage[k], chunk);
+    }
+    dev_free(d, m->stream);
+    throw;
+  }
+  for (int k = 0; k < 2; k++) {
+    cudaEventDestroy(done[k]);
+    g_pinned.put(stage[k], chunk);
+  }
   return (float*)d;
 }
 
