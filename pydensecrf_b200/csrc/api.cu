@@ -14,6 +14,7 @@
 #include <map>
 #include <memory>
 #include <atomic>
+#include <condition_variable>
 #include <mutex>
 #include <thread>
 
@@ -618,20 +619,63 @@ void mat_written(dcrf_model* m, dcrf_mat* a) {
 // dcrf_host_alloc) goes by DMA at PCIe rate (~53 GB/s).  Ordinary pageable memory -- what a numpy array is -- would
 // reach the device at ~10 GB/s through the driver's own staging copy, so large pageable uploads are staged here: a few
 // threads memcpy the next chunk into one of two page-locked buffers while the previous chunk is on the bus.
-static void parallel_memcpy(char* dst, const char* src, size_t n, int nthreads) {
-  if (nthreads <= 1 || n < (1u << 20)) {
-    std::memcpy(dst, src, n);
-    return;
+// Helper threads for those memcpys: started on first use and kept (a thread start per chunk would cost more than a small
+// upload takes).  One upload at a time drives them; a second concurrent upload just copies on its own thread.
+class CopyPool {
+ public:
+  void copy(char* dst, const char* src, size_t n, int nthreads) {
+    std::unique_lock<std::mutex> own(owner_, std::try_to_lock);
+    if (!own.owns_lock() || nthreads <= 1 || n < (1u << 20)) {
+      std::memcpy(dst, src, n);
+      return;
+    }
+    std::unique_lock<std::mutex> lk(mu_);
+    while (nhelpers_ < nthreads - 1) {
+      std::thread([this] { worker(); }).detach();
+      nhelpers_++;
+    }
+    dst_ = dst, src_ = src, n_ = n;
+    parts_ = nthreads;
+    per_ = ((n + parts_ - 1) / parts_ + 63) & ~(size_t)63;
+    next_ = 0, done_ = 0;
+    gen_++;
+    cv_.notify_all();
+    take_parts(lk);
+    cv_done_.wait(lk, [&] { return done_ == parts_; });
   }
-  const size_t per = ((n + nthreads - 1) / nthreads + 63) & ~(size_t)63;
-  std::vector<std::thread> th;
-  for (int k = 1; k < nthreads; k++) {
-    const size_t o = (size_t)k * per;
-    if (o < n) th.emplace_back([=] { std::memcpy(dst + o, src + o, std::min(per, n - o)); });
+
+ private:
+  void take_parts(std::unique_lock<std::mutex>& lk) {  // called with mu_ held
+    while (next_ < parts_) {
+      const int p = next_++;
+      const size_t o = (size_t)p * per_;
+      char* d = dst_;
+      const char* s = src_;
+      const size_t len = o < n_ ? std::min(per_, n_ - o) : 0;
+      lk.unlock();
+      if (len) std::memcpy(d + o, s + o, len);
+      lk.lock();
+      if (++done_ == parts_) cv_done_.notify_all();
+    }
   }
-  std::memcpy(dst, src, std::min(per, n));
-  for (auto& t : th) t.join();
-}
+  void worker() {
+    uint64_t seen = 0;
+    std::unique_lock<std::mutex> lk(mu_);
+    for (;;) {
+      cv_.wait(lk, [&] { return gen_ != seen; });
+      seen = gen_;
+      take_parts(lk);
+    }
+  }
+  std::mutex owner_, mu_;
+  std::condition_variable cv_, cv_done_;
+  char* dst_ = nullptr;
+  const char* src_ = nullptr;
+  size_t n_ = 0, per_ = 0;
+  int parts_ = 0, next_ = 0, done_ = 0, nhelpers_ = 0;
+  uint64_t gen_ = 0;
+};
+static CopyPool& g_copy_pool = *new CopyPool();  // never destroyed: its detached helpers may outlive static destructors
 
 float* upload_tmp(dcrf_model* m, const void* host, size_t bytes) {
   char* d = dev_alloc<char>(bytes, m->stream);
@@ -642,12 +686,12 @@ float* upload_tmp(dcrf_model* m, const void* host, size_t bytes) {
   cudaPointerAttributes at{};
   const bool pageable = cudaPointerGetAttributes(&at, host) != cudaSuccess || at.type == cudaMemoryTypeUnregistered;
   cudaGetLastError();
-  if (!pageable || nthreads == 0 || bytes < (16u << 20)) {  // below ~16 MB the thread start-up costs more than it saves
+  if (!pageable || nthreads == 0 || bytes < (4u << 20)) {
     DCRF_CUDA(cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, m->stream));
     return (float*)d;
   }
   const size_t mb = 1u << 20;
-  const size_t chunk = std::min((size_t)32 * mb, std::max((size_t)4 * mb, ((bytes / 4 + mb - 1) / mb) * mb));
+  const size_t chunk = std::min((size_t)32 * mb, std::max((size_t)2 * mb, ((bytes / 4 + mb - 1) / mb) * mb));
   char* stage[2] = {(char*)g_pinned.get(chunk), (char*)g_pinned.get(chunk)};
   cudaEvent_t done[2] = {nullptr, nullptr};
   try {
@@ -656,7 +700,7 @@ float* upload_tmp(dcrf_model* m, const void* host, size_t bytes) {
     for (size_t off = 0; off < bytes; off += chunk, i++) {
       const size_t n = std::min(chunk, bytes - off);
       if (i >= 2) DCRF_CUDA(cudaEventSynchronize(done[i & 1]));  // the DMA that last read this staging buffer
-      parallel_memcpy(stage[i & 1], (const char*)host + off, n, nthreads);
+      g_copy_pool.copy(stage[i & 1], (const char*)host + off, n, nthreads);
       DCRF_CUDA(cudaMemcpyAsync(d + off, stage[i & 1], n, cudaMemcpyHostToDevice, m->stream));
       DCRF_CUDA(cudaEventRecord(done[i & 1], m->stream));
     }
