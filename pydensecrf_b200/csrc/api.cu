@@ -1276,6 +1276,33 @@ dcrf_status dcrf_mat_host_ptr(dcrf_mat_t* a, float** ptr) {
     *ptr = a->host;
   });
 }
+dcrf_status dcrf_mat_argmax(dcrf_mat_t* a, int16_t* labels_cols) {
+  return guarded([&] {
+    DCRF_REQUIRE(a && labels_cols, "null argument");
+    DCRF_REQUIRE(a->dev && a->dev_valid, "matrix has no current device copy (it was created or modified on the host)");
+    DCRF_REQUIRE(a->rows >= 1 && a->rows <= 32767, "bad label count for a label map");
+    DeviceGuard g(a->device);
+    cudaStream_t s;
+    DCRF_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    int16_t* d = nullptr;
+    try {
+      DCRF_CUDA(cudaStreamWaitEvent(s, a->ready, 0));  // order after the producer without needing its stream
+      Profiler none;
+      d = dev_alloc<int16_t>((size_t)a->cols, s);
+      launch_argmax(Ctx{s, &none}, RowLayout(a->rows), a->cols, a->dev, d);
+      DCRF_CUDA(cudaGetLastError());
+      DCRF_CUDA(cudaMemcpyAsync(labels_cols, d, (size_t)a->cols * sizeof(int16_t), cudaMemcpyDeviceToHost, s));
+      DCRF_CUDA(cudaEventRecord(a->ready, s));  // a later writer / free has to wait for this read
+      dev_free(d, s);
+      DCRF_CUDA(cudaStreamSynchronize(s));
+    } catch (...) {
+      cudaStreamSynchronize(s);
+      cudaStreamDestroy(s);
+      throw;
+    }
+    cudaStreamDestroy(s);
+  });
+}
 dcrf_status dcrf_mat_device_ptr(dcrf_mat_t* a, float** ptr, int* pitch_floats, int* device) {
   return guarded([&] {
     DCRF_REQUIRE(a && ptr && pitch_floats && device, "null argument");

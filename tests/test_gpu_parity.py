@@ -726,3 +726,39 @@ def test_gaussian_lattice_is_shared_between_models(dcrf, po):
     e.addPairwiseGaussian(sxy=(5, 5), compat=1)   # second geometry: its own lattice
     assert e._lattice_info(0)[2] != e._lattice_info(1)[2]
     assert np.isfinite(np.array(e.inference(2))).all()
+
+
+def test_numpy_argmax_on_a_result_runs_on_the_device(dcrf):
+    """`np.argmax(Q, axis=0)` (the reference's own post-processing line) dispatches to the device argmax while Q lives on
+    the GPU and gives exactly NumPy's answer; everything else NumPy does with a MatrixXf is unchanged."""
+    import pydensecrf_b200.eigen as eigen
+    from tests import workloads as wl
+
+    W, H, L = 61, 43, 21
+    d = dcrf.DenseCRF2D(W, H, L)
+    d.setUnaryEnergy(wl.softmax_unary(H, W, L, seed=2, grid=8))
+    d.addPairwiseGaussian(sxy=3, compat=3)
+    d.addPairwiseBilateral(sxy=40, srgb=13, rgbim=wl.smooth_image(H, W, seed=2, grid=8), compat=10)
+    Q = d.inference(5)
+    assert Q._argmax_device() is not None                 # still on the device
+    m = np.argmax(Q, axis=0)
+    assert m.dtype == np.intp and m.shape == (H * W,)
+    Qh = np.array(Q)
+    assert np.array_equal(m, np.argmax(Qh, axis=0))
+    assert np.array_equal(m, d.currentMap(Q))
+    assert np.array_equal(np.argmax(Q, 0), m)             # positional axis
+    # other axes / functions take NumPy's own implementation on the buffer view
+    assert np.array_equal(np.argmax(Q, axis=1), np.argmax(Qh, axis=1))
+    assert np.argmax(Q) == np.argmax(Qh)
+    assert np.isclose(np.sum(Q), Qh.sum()) and np.allclose(np.max(Q, axis=0), Qh.max(0))
+    assert np.stack([Q, Q]).shape == (2, L, H * W)
+    # a matrix that only exists on the host is left to NumPy
+    Mh = eigen.matrixXf(np.ascontiguousarray(Qh))
+    assert Mh._argmax_device() is None
+    assert np.array_equal(np.argmax(Mh, axis=0), np.argmax(Qh, axis=0))
+    # a view that was written through invalidates the device copy: NumPy's path must see the edit
+    v = np.asarray(Q)
+    v[:, 0] = 0.0
+    v[3, 0] = 1.0
+    del v
+    assert np.argmax(Q, axis=0)[0] == 3
