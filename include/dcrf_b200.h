@@ -148,9 +148,10 @@ int dcrf_mat_cols(const dcrf_mat_t* a);
  * ends so the next device use re-uploads. */
 dcrf_status dcrf_mat_host_ptr(dcrf_mat_t* a, float** ptr);
 /* Column-wise argmax of a matrix whose current contents are on the device (a result of inference / stepInference):
- * labels_cols receives `cols` int16, first maximum wins -- what np.argmax(Q, axis=0) computes (examples/inference.py:122,
- * README.md:199), without moving Q to the host.  DCRF_EINVAL if the matrix only exists on the host. */
-dcrf_status dcrf_mat_argmax(dcrf_mat_t* a, int16_t* labels_cols);
+ * labels_cols receives `cols` labels of label_bytes bytes each (2: int16, 8: int64 = what np.argmax returns), first
+ * maximum wins -- what np.argmax(Q, axis=0) computes (examples/inference.py:122, README.md:199), without moving Q to the
+ * host.  DCRF_EINVAL if the matrix only exists on the host. */
+dcrf_status dcrf_mat_argmax(dcrf_mat_t* a, void* labels_cols, int label_bytes);
 /* device view of a result matrix for GPU-resident consumers (exposed as __cuda_array_interface__ by the binding):
  * cols rows of *pitch_floats floats, the first `rows` of each row are the labels of one variable.  Valid until the
  * matrix is destroyed or written again; fails if the current contents only exist on the host. */

@@ -62,7 +62,7 @@ cdef extern from "dcrf_b200.h" nogil:
     int dcrf_profile_read(dcrf_t* m, dcrf_prof_entry* out, int cap, int* n, int reset)
     int64_t dcrf_launch_count(const dcrf_t* m)
     int dcrf_flush_l2(dcrf_t* m)
-    int dcrf_mat_argmax(dcrf_mat_t* a, int16_t* labels)
+    int dcrf_mat_argmax(dcrf_mat_t* a, void* labels, int label_bytes)
     int dcrf_debug_selftest(dcrf_t* m, int which, uint64_t n, uint64_t seed, uint64_t* mismatches)
     int dcrf_batch_map_2d(int W, int H, int L, int device, int B, const float* const* unary, const uint8_t* const* rgb,
                           float g_sx, float g_sy, float g_w, float b_sx, float b_sy, float b_sr, float b_sg, float b_sb,
@@ -292,17 +292,19 @@ cdef class MatrixXf:
         if self.h != NULL:
             dcrf_mat_release_host(self.h)
 
-    def _argmax_device(self):
-        """Column-wise argmax on the GPU (int16, length cols), or None when the current contents are on the host."""
+    def _argmax_device(self, bint wide=False):
+        """Column-wise argmax on the GPU (int16, or int64 if `wide`; length cols), or None when the current contents
+        are on the host."""
         import numpy as np
         if self.h == NULL or self.shape[1] == 0:
             return None
-        out = np.empty(self.shape[1], dtype=np.int16)
-        cdef int16_t[::1] o = out
+        # page-locked (pooled) result memory: the label map arrives by DMA at PCIe rate
+        out = pinned_empty((self.shape[1],), np.int64 if wide else np.int16)
+        cdef size_t addr = out.ctypes.data
         cdef dcrf_mat_t* h = self.h
-        cdef int st
+        cdef int st, nb = 8 if wide else 2
         with nogil:
-            st = dcrf_mat_argmax(h, &o[0])
+            st = dcrf_mat_argmax(h, <void*>addr, nb)
         if st == 1:      # DCRF_EINVAL: no current device copy
             return None
         _check(st)
@@ -318,9 +320,9 @@ cdef class MatrixXf:
                 and kwargs.get("out") is None and not kwargs.get("keepdims", False):
             axis = args[1] if len(args) == 2 else kwargs.get("axis", None)
             if axis is not None and not isinstance(axis, bool) and int(axis) in (0, -2) and self.shape[0] > 0:
-                lab = self._argmax_device()
+                lab = self._argmax_device(wide=True)     # int64 straight from the device: no host-side conversion pass
                 if lab is not None:
-                    return lab.astype(np.intp)
+                    return lab if lab.dtype == np.intp else lab.astype(np.intp)
         impl = getattr(func, "_implementation", None)
         if impl is None:
             return NotImplemented
@@ -688,7 +690,7 @@ cdef class DenseCRF:
         """Per-variable argmax of Q computed on the device (DenseCRF::currentMap, densecrf.cpp:202-211):
         int16 array of length nvar; only 2 bytes per variable cross PCIe instead of the 4*nlabels of Q."""
         import numpy as np
-        out = np.empty(self._nvar, dtype=np.int16)
+        out = pinned_empty((self._nvar,), np.int16)
         cdef int16_t[::1] o = out
         cdef dcrf_mat_t* q = Q.handle()
         cdef int st

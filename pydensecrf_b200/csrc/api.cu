@@ -1288,22 +1288,26 @@ dcrf_status dcrf_mat_host_ptr(dcrf_mat_t* a, float** ptr) {
     *ptr = a->host;
   });
 }
-dcrf_status dcrf_mat_argmax(dcrf_mat_t* a, int16_t* labels_cols) {
+dcrf_status dcrf_mat_argmax(dcrf_mat_t* a, void* labels_cols, int label_bytes) {
   return guarded([&] {
     DCRF_REQUIRE(a && labels_cols, "null argument");
+    DCRF_REQUIRE(label_bytes == 2 || label_bytes == 8, "labels are int16 (label_bytes = 2) or int64 (8)");
     DCRF_REQUIRE(a->dev && a->dev_valid, "matrix has no current device copy (it was created or modified on the host)");
     DCRF_REQUIRE(a->rows >= 1 && a->rows <= 32767, "bad label count for a label map");
     DeviceGuard g(a->device);
     cudaStream_t s;
     DCRF_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
-    int16_t* d = nullptr;
+    char* d = nullptr;
     try {
       DCRF_CUDA(cudaStreamWaitEvent(s, a->ready, 0));  // order after the producer without needing its stream
       Profiler none;
-      d = dev_alloc<int16_t>((size_t)a->cols, s);
-      launch_argmax(Ctx{s, &none}, RowLayout(a->rows), a->cols, a->dev, d);
+      d = dev_alloc<char>((size_t)a->cols * label_bytes, s);
+      if (label_bytes == 2)
+        launch_argmax(Ctx{s, &none}, RowLayout(a->rows), a->cols, a->dev, (int16_t*)d);
+      else
+        launch_argmax64(Ctx{s, &none}, RowLayout(a->rows), a->cols, a->dev, (long long*)d);
       DCRF_CUDA(cudaGetLastError());
-      DCRF_CUDA(cudaMemcpyAsync(labels_cols, d, (size_t)a->cols * sizeof(int16_t), cudaMemcpyDeviceToHost, s));
+      DCRF_CUDA(cudaMemcpyAsync(labels_cols, d, (size_t)a->cols * label_bytes, cudaMemcpyDeviceToHost, s));
       DCRF_CUDA(cudaEventRecord(a->ready, s));  // a later writer / free has to wait for this read
       dev_free(d, s);
       DCRF_CUDA(cudaStreamSynchronize(s));

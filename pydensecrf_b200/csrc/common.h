@@ -260,5 +260,6 @@ void launch_logistic_unary(Ctx cx, RowLayout rl, int N, int F, const float* Lmat
 // sums[0] += sum Q log max(Q,1e-20), sums[1] += sum U*Q, sums[2] += sum Q*T   (double accumulators on the device)
 void launch_kl_terms(Ctx cx, RowLayout rl, int N, const float* Q, const float* U, const float* T, double* sums);
 void launch_argmax(Ctx cx, RowLayout rl, int N, const float* Q, int16_t* labels);
+void launch_argmax64(Ctx cx, RowLayout rl, int N, const float* Q, long long* labels);
 
 }  // namespace dcrf
