@@ -125,11 +125,13 @@ dcrf_status dcrf_current_map(dcrf_t* m, dcrf_mat_t* Q, int16_t* labels_N);
  * (examples/inference.py:69-122; Potts compatibilities, NORMALIZE_SYMMETRIC) -- from n_workers host threads (0 = 4), each
  * with its own model and stream, so that lattice construction, uploads and kernels of different images overlap on the
  * device.  Results are identical to the per-image calls.  labels[b] receives N int16; q_out (may be NULL) points to B
- * arrays of L*N floats that receive Q in the (L, N) row-major layout of np.array(Q). */
+ * arrays of L*N floats that receive Q in the (L, N) row-major layout of np.array(Q).
+ * Several GPUs (replicas, no collective): devices[0..n_devices) lists them and worker k drives devices[k %
+ * n_devices] (n_workers then defaults to 4 per device); with devices == NULL everything runs on `device` (-1 = default). */
 dcrf_status dcrf_batch_map_2d(int W, int H, int L, int device, int B, const float* const* unary_LxN,
                               const uint8_t* const* rgb_HxWx3, float g_sx, float g_sy, float g_w, float b_sx, float b_sy,
                               float b_sr, float b_sg, float b_sb, float b_w, int n_iterations, int n_workers,
-                              int16_t* const* labels, float* const* q_out);
+                              int16_t* const* labels, float* const* q_out, const int* devices, int n_devices);
 
 /* ---- matrices: the eigen.MatrixXf / eigen.VectorXf objects of the reference -------------------- */
 /* replaces eigen.MatrixXf() (empty 0x0)               pydensecrf/eigen.pyx:62-66 */

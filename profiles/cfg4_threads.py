@@ -45,3 +45,10 @@ for nw in (1, 4, 8):
     t0 = time.perf_counter(); lab = dcrf.map_batch_2d(Ub, Ib, n_iter=5, workers=nw); dt = time.perf_counter() - t0
     assert np.array_equal(lab[1].ravel(), ref)
     print("cfg4 one GPU, map_batch_2d(workers=%d): %.0f images/s (%.2f ms per image)" % (nw, Bn / dt, dt / Bn * 1e3))
+
+if dcrf.device_count() > 1:
+    devs = list(range(dcrf.device_count()))
+    dcrf.map_batch_2d(Ub[:32], Ib[:32], n_iter=5, device=devs)
+    t0 = time.perf_counter(); lab = dcrf.map_batch_2d(Ub, Ib, n_iter=5, device=devs); dt = time.perf_counter() - t0
+    assert np.array_equal(lab[1].ravel(), ref)
+    print("cfg4 %d GPUs, map_batch_2d(device=%s): %.0f images/s (%.2f ms per image)" % (len(devs), devs, Bn / dt, dt / Bn * 1e3))

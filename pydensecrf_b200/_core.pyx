@@ -66,7 +66,8 @@ cdef extern from "dcrf_b200.h" nogil:
     int dcrf_debug_selftest(dcrf_t* m, int which, uint64_t n, uint64_t seed, uint64_t* mismatches)
     int dcrf_batch_map_2d(int W, int H, int L, int device, int B, const float* const* unary, const uint8_t* const* rgb,
                           float g_sx, float g_sy, float g_w, float b_sx, float b_sy, float b_sr, float b_sg, float b_sb,
-                          float b_w, int n_iterations, int n_workers, int16_t* const* labels, float* const* q_out)
+                          float b_w, int n_iterations, int n_workers, int16_t* const* labels, float* const* q_out,
+                          const int* devices, int n_devices)
     int dcrf_num_pairwise(const dcrf_t* m)
     int dcrf_lattice_info(const dcrf_t* m, int k, int* d, int* N, int* V)
     int dcrf_lattice_dump(dcrf_t* m, int k, int32_t* offset, float* bary, int16_t* keys, int32_t* nbr, float* norm)
@@ -410,15 +411,16 @@ cdef class LogisticUnary(Unary):
 
 
 def map_batch_2d(float[:, :, ::1] unaries not None, unsigned char[:, :, :, ::1] images not None, sxy_gaussian=3,
-                 compat_gaussian=3, sxy_bilateral=80, srgb=13, compat_bilateral=10, int n_iter=5, int workers=4,
+                 compat_gaussian=3, sxy_bilateral=80, srgb=13, compat_bilateral=10, int n_iter=5, int workers=0,
                  device=None, bint return_q=False):
     """MAP labelling of a batch of images of one size with shared kernel parameters (SURVEY 8f-3, BASELINE cfg 4).
 
     unaries: (B, nlabels, H*W) float32, images: (B, H, W, 3) uint8.  Per image this is DenseCRF2D(W, H, nlabels) +
     setUnaryEnergy + addPairwiseGaussian(sxy_gaussian, compat_gaussian) + addPairwiseBilateral(sxy_bilateral, srgb,
     image, compat_bilateral) + inference(n_iter) + argmax, with identical results, but the images are spread over
-    `workers` host threads inside the library (each with its own model and CUDA stream), so that lattice construction,
-    uploads and kernels of different images overlap.  Returns (B, H, W) int16 labels, and Q (B, nlabels, H*W) float32 as
+    `workers` host threads inside the library (each with its own model and CUDA stream; default 4 per GPU), so that
+    lattice construction, uploads and kernels of different images overlap.  `device` may be a list of GPU indices: the
+    workers are then spread over those GPUs (independent replicas, no collective).  Returns (B, H, W) int16 labels, and Q (B, nlabels, H*W) float32 as
     well if return_q.  Inputs in page-locked memory (utils.pinned_empty) upload about five times faster."""
     import numpy as np
     cdef int B = <int>unaries.shape[0], L = <int>unaries.shape[1]
@@ -446,7 +448,20 @@ def map_batch_2d(float[:, :, ::1] unaries not None, unsigned char[:, :, :, ::1] 
     cdef int16_t** lp = <int16_t**>malloc(max(B, 1) * sizeof(void*))
     cdef float** qp = <float**>malloc(max(B, 1) * sizeof(void*))
     cdef int b, st
-    cdef int dev = -1 if device is None else int(device)
+    cdef int dev = -1
+    cdef int ndev = 0
+    cdef int devs[64]
+    cdef const int* dp = NULL
+    if device is not None:
+        if isinstance(device, (list, tuple)):
+            if not 1 <= len(device) <= 64:
+                raise ValueError("device list must name 1..64 GPUs")
+            ndev = len(device)
+            for b in range(ndev):
+                devs[b] = int(device[b])
+            dp = devs
+        else:
+            dev = int(device)
     cdef float gsx = sxy_gaussian[0], gsy = sxy_gaussian[1], gw = compat_gaussian
     cdef float bsx = sxy_bilateral[0], bsy = sxy_bilateral[1], sr = srgb[0], sg = srgb[1], sb = srgb[2], bw = compat_bilateral
     try:
@@ -459,7 +474,7 @@ def map_batch_2d(float[:, :, ::1] unaries not None, unsigned char[:, :, :, ::1] 
             qp[b] = &q_v[b, 0, 0] if return_q else NULL
         with nogil:
             st = dcrf_batch_map_2d(W, H, L, dev, B, up, ip, gsx, gsy, gw, bsx, bsy, sr, sg, sb, bw, n_iter, workers,
-                                   lp, qp if return_q else NULL)
+                                   lp, qp if return_q else NULL, dp, ndev)
         _check(st)
     finally:
         free(up)

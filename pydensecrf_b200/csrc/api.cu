@@ -1420,11 +1420,14 @@ dcrf_status dcrf_flush_l2(dcrf_t* m) {
 dcrf_status dcrf_batch_map_2d(int W, int H, int L, int device, int B, const float* const* unary_LxN,
                               const uint8_t* const* rgb_HxWx3, float g_sx, float g_sy, float g_w, float b_sx, float b_sy,
                               float b_sr, float b_sg, float b_sb, float b_w, int n_iterations, int n_workers,
-                              int16_t* const* labels, float* const* q_out) {
+                              int16_t* const* labels, float* const* q_out, const int* devices, int n_devices) {
   return guarded([&] {
     DCRF_REQUIRE(W > 0 && H > 0 && L > 0 && B >= 0 && n_iterations >= 0, "bad batch shape");
     DCRF_REQUIRE(B == 0 || (unary_LxN && rgb_HxWx3 && labels), "null argument");
-    const int nw = std::max(1, std::min(n_workers > 0 ? n_workers : 4, B));
+    DCRF_REQUIRE(n_devices >= 0 && (n_devices == 0 || devices), "bad device list");
+    const int ndev = devices ? std::max(n_devices, 1) : 1;
+    const int nw = std::max(1, std::min(n_workers > 0 ? n_workers : 4 * ndev, B));
+    std::atomic<int> next_worker{0};
     std::atomic<int> next{0};
     std::atomic<bool> failed{false};
     std::mutex mu;
@@ -1432,12 +1435,14 @@ dcrf_status dcrf_batch_map_2d(int W, int H, int L, int device, int B, const floa
     dcrf_status first_status = DCRF_OK;
     auto worker = [&] {
       const size_t N = (size_t)W * H;
+      const int wk = next_worker.fetch_add(1);
+      const int dev = (devices && n_devices > 0) ? devices[wk % n_devices] : device;
       for (;;) {
         const int b = next.fetch_add(1);
         if (b >= B || failed.load()) return;
         dcrf_t* m = nullptr;
         dcrf_mat_t* Q = nullptr;
-        dcrf_status st = dcrf_create_2d(W, H, L, device, &m);
+        dcrf_status st = dcrf_create_2d(W, H, L, dev, &m);
         if (st == DCRF_OK) st = dcrf_set_unary_const(m, unary_LxN[b]);
         if (st == DCRF_OK) st = dcrf_add_pairwise_gaussian(m, g_sx, g_sy, DCRF_COMPAT_POTTS, &g_w, 1, DCRF_NORMALIZE_SYMMETRIC);
         if (st == DCRF_OK)

@@ -548,6 +548,12 @@ def test_two_devices_in_one_process(dcrf):
         d.addPairwiseBilateral(80, 13, img, 10.0)
         res.append(np.array(d.inference(5)))
     assert np.array_equal(res[0], res[1])
+    # the batch entry spread over both GPUs returns what one GPU returns
+    Ub = np.stack([wl.softmax_unary(H, W, L, seed=b, grid=8) for b in range(10)])
+    Ib = np.stack([wl.smooth_image(H, W, seed=b, grid=8) for b in range(10)])
+    one = dcrf.map_batch_2d(Ub, Ib, n_iter=3, device=0)
+    two = dcrf.map_batch_2d(Ub, Ib, n_iter=3, device=[0, 1], workers=4)
+    assert np.array_equal(one, two)
 
 
 def test_device_resident_io_with_torch(dcrf):
