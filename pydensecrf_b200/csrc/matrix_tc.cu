@@ -19,6 +19,7 @@
 // shared-memory tile that aliases the operand stages, then all threads apply tmp1 -= out (or write out) with
 // coalesced row accesses.
 #include <algorithm>
+#include <cstdio>
 
 #include "common.h"
 #include "softmax_math.cuh"
@@ -297,6 +298,9 @@ __global__ void __launch_bounds__(kTCThreads, 2) k_update_matrix_tc(TCUArgs a) {
   const int gslabs = nslabs * a.nterms;   // per tile
   const int ntiles = (a.N + kTM - 1) / kTM;
   uint32_t it = 0, tl = 0;
+#ifdef TCU_TIMING  // -DTCU_TIMING: block 0 prints the clock64 cycles per tile spent in each phase (profiles/build_variant.py)
+  long long t_main = 0, t_stage = 0, t_soft = 0, t_mark = clock64();
+#endif
 
   static_assert(kTM * kCH == kTCThreads, "one A chunk per thread");
   constexpr int kNB = (256 * kCH + kTCThreads - 1) / kTCThreads;
@@ -366,6 +370,9 @@ __global__ void __launch_bounds__(kTCThreads, 2) k_update_matrix_tc(TCUArgs a) {
         if (g == gslabs - 1) umma_commit(smem_u32(bars + 2));
       }
     }
+#ifdef TCU_TIMING
+    { const long long n = clock64(); t_main += n - t_mark; t_mark = n; }
+#endif
     // ---- epilogue: accumulator -> shared-memory tile -> x = (-U) - acc -> column softmax -> Q ------------------
     mbar_wait(smem_u32(bars + 2), tl & 1);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -395,6 +402,9 @@ __global__ void __launch_bounds__(kTCThreads, 2) k_update_matrix_tc(TCUArgs a) {
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();  // tile complete in shared memory; TMEM may be overwritten by the next tile's MMAs
+#ifdef TCU_TIMING
+    { const long long n = clock64(); t_stage += n - t_mark; t_mark = n; }
+#endif
     {
       const unsigned full = 0xffffffffu;
       const int L = a.L, nfull = L / 4;
@@ -451,9 +461,15 @@ __global__ void __launch_bounds__(kTCThreads, 2) k_update_matrix_tc(TCUArgs a) {
       }
     }
     __syncthreads();  // the tile has been consumed: the next tile may refill the operand stages
+#ifdef TCU_TIMING
+    { const long long n = clock64(); t_soft += n - t_mark; t_mark = n; }
+#endif
   }
 
   __syncthreads();
+#ifdef TCU_TIMING
+  if (tid == 0 && blockIdx.x == 0) printf("[tcu] tiles %u: mainloop %lld, tmem->smem %lld, softmax %lld cycles per tile\n", tl, t_main / max(tl, 1u), t_stage / max(tl, 1u), t_soft / max(tl, 1u));
+#endif
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
 }
 
