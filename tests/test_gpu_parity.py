@@ -683,6 +683,18 @@ def test_map_batch_2d_equals_per_image_calls(dcrf):
         Qb = d.inference(5)
         assert np.array_equal(Q[b], np.array(Qb))
         assert np.array_equal(labels[b].ravel(), d.currentMap(Qb))
+    # unaries above 4 MB take the staged upload (page-locked double buffer + copy pool): several workers at once
+    W2, H2, L2 = 256, 256, 21
+    U2 = np.stack([wl.softmax_unary(H2, W2, L2, seed=b, grid=8) for b in range(6)])
+    I2 = np.stack([wl.smooth_image(H2, W2, seed=b, grid=8) for b in range(6)])
+    assert U2[0].nbytes > (4 << 20)
+    lab2 = dcrf.map_batch_2d(U2, I2, n_iter=3, workers=4)
+    for b in range(6):
+        d = dcrf.DenseCRF2D(W2, H2, L2)
+        d.setUnaryEnergy(U2[b])
+        d.addPairwiseGaussian(sxy=3, compat=3)
+        d.addPairwiseBilateral(sxy=80, srgb=13, rgbim=I2[b], compat=10)
+        assert np.array_equal(lab2[b].ravel(), d.currentMap(d.inference(3)))
     only = dcrf.map_batch_2d(U[:2], I[:2], n_iter=2, workers=1)
     assert only.shape == (2, H, W)
     assert dcrf.map_batch_2d(U[:0], I[:0]).shape == (0, H, W)
