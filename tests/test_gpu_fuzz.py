@@ -122,3 +122,31 @@ def test_random_generic_models_match_the_oracle(dcrf, po, seed):
     Q = np.array(d.inference(n_it))
     err = np.abs(Q - Qo).max()
     assert np.isfinite(Q).all() and err <= Q_ATOL, (seed, N, L, err)
+
+
+def test_extreme_unaries_match_the_oracle(dcrf, po):
+    """Huge, tiny and equal energies: the clamp of Eigen's exp (x >= -88.376), columns whose entries are all equal, and
+    energies far outside float's exp range behave as in the reference (no NaN, same Q)."""
+    from tests import workloads as wl
+
+    W, H, L = 24, 17, 21
+    rng = np.random.default_rng(77)
+    U = rng.uniform(0, 5, (L, H * W)).astype(np.float32)
+    U[:, 0] = 0.0                    # all labels equal
+    U[:, 1] = 1e30                   # all huge and equal
+    U[3, 2] = 1e30                   # one label impossible
+    U[:, 3] = np.linspace(0, 200, L)  # spans far beyond exp's range: the clamp decides
+    U[:, 4] = 88.0 + np.arange(L, dtype=np.float32) * 0.1
+    U[5, 5] = -1e4                   # one label overwhelmingly likely
+    img = wl.smooth_image(H, W, seed=1, grid=4)
+    d = dcrf.DenseCRF2D(W, H, L)
+    o = po.CRF((W, H), L, "orc")
+    for c in (d, o):
+        c.setUnaryEnergy(U)
+        c.addPairwiseGaussian((3, 3), 3.0)
+        c.addPairwiseBilateral((20, 20), (13, 13, 13), img, 10.0)
+    for n_it in (0, 1, 3):
+        Q = np.array(d.inference(n_it))
+        Qo = o.inference(n_it)
+        assert np.isfinite(Q).all() and np.isfinite(Qo).all()
+        assert np.abs(Q - Qo).max() <= Q_ATOL, n_it
