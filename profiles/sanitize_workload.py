@@ -23,4 +23,14 @@ for L, compat in [(21, 3.0), (2, 3.0), (5, None), (70, "m"), (150, "m")]:
     d.setSoftmaxMode(True); d.inference(1); d.setSoftmaxMode(False)
     d._set_iteration_mode(1); d.inference(1)
     print(L, float(np.asarray(Q).sum()), kl, int(m.sum()))
+# batch entry (worker threads, shared Gaussian lattice), NumPy argmax dispatch (int64 device argmax), staged upload (> 4 MB)
+Ub = np.stack([wl.softmax_unary(H, W, 7, seed=b, grid=8) for b in range(5)])
+Ib = np.stack([wl.smooth_image(H, W, seed=b, grid=8) for b in range(5)])
+lab = dcrf.map_batch_2d(Ub, Ib, n_iter=2, workers=3)
+d = dcrf.DenseCRF2D(256, 256, 21)
+d.setUnaryEnergy(wl.softmax_unary(256, 256, 21, seed=1, grid=8))
+d.addPairwiseGaussian(3, 3.0)
+m2 = np.argmax(d.inference(1), axis=0)
+assert d._selftest(1, n=100000, seed=3) == 0
+print(int(lab.sum()), int(m2.sum()))
 print("sanitize-ok")
