@@ -59,4 +59,20 @@ __device__ __forceinline__ float tail_exp_nonpos(float xf) {
   return (float)__hiloint2double(hi, __double2loint(p));
 }
 
+// b / s for the elements of a column that share the divisor: the instruction sequence of the IEEE division
+// fast path (reciprocal refined once, quotient refined once from the exact remainder) with the reciprocal
+// computed once.  Valid while no intermediate can leave the normal range; callers guarantee 1 <= s <= 2^8 and
+// take __fdiv_rn for any numerator below 2^-63 (checked against __fdiv_rn by dcrf_debug_selftest).
+__device__ __forceinline__ float refined_rcp(float s) {
+  float r0;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(s));
+  const float e = __fmaf_rn(-s, r0, 1.f);
+  return __fmaf_rn(r0, e, r0);
+}
+__device__ __forceinline__ float div_shared(float b, float s, float r) {
+  const float q0 = __fmaf_rn(b, r, 0.f);
+  const float rem = __fmaf_rn(-s, q0, b);
+  return __fmaf_rn(r, rem, q0);
+}
+
 }  // namespace dcrf
