@@ -873,8 +873,12 @@ void launch_update_matrix_tc(Ctx cx, RowLayout rl, TCUArgs a) {
     const int ku = (rl.L + 31) / 32;
     if (ku <= 2)
       go(k_update_matrix_tc_ws<2>);
+    else if (ku <= 3)
+      go(k_update_matrix_tc_ws<3>);
     else if (ku <= 4)
       go(k_update_matrix_tc_ws<4>);
+    else if (ku <= 5)
+      go(k_update_matrix_tc_ws<5>);  // 129..160 labels (ADE20K's 150)
     else if (ku <= 6)
       go(k_update_matrix_tc_ws<6>);
     else
