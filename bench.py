@@ -111,6 +111,29 @@ def dist_setup(n_gpus, backend="nccl"):
     return 1, 0, 0, None, None
 
 
+def bind_to_gpu_numa(local):
+    """Pin this rank to the CPUs next to its GPU (NVML's ideal affinity) before any page-locked buffer is allocated, so that
+    the host side of every PCIe copy is local memory: with 8 ranks on a two-socket host the copies otherwise cross the
+    socket interconnect.  Best effort; DCRF_BENCH_NO_AFFINITY=1 turns it off.  Returns a short description."""
+    if os.environ.get("DCRF_BENCH_NO_AFFINITY"):
+        return "off"
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        allowed = os.sched_getaffinity(0)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (max(allowed) + 64) // 64)
+        ideal = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        target = ideal & allowed
+        if not target or target == allowed:
+            return "unchanged (%d cpus)" % len(allowed)
+        os.sched_setaffinity(0, target)
+        return "%d of %d cpus" % (len(target), len(allowed))
+    except Exception as e:  # noqa: BLE001
+        return "unavailable (%s)" % type(e).__name__
+
+
 def shard_of(rank, world, n_units):
     """Units (images) a rank owns when a batch is split over replicas: contiguous blocks, remainder to the
     first ranks.  bench's 1080p workload uses one image per rank (seed = rank); cfg 4 style batches use this."""
@@ -173,6 +196,7 @@ def kernel_bytes(name, lat):
 
 def run_b200(args):
     world, rank, local, dist, torch = dist_setup(args.gpus)
+    affinity = bind_to_gpu_numa(local)
     import pydensecrf_b200.densecrf as dcrf
     import pydensecrf_b200.eigen as eigen
 
@@ -368,6 +392,7 @@ def run_b200(args):
            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": WORKLOAD, "image": "smooth synthetic (seed=rank)", "replicas": world,
+                      "cpu_affinity": affinity,
                       "lattice_vertices": {"gaussian": lat[0][1], "bilateral": lat[1][1]},
                       "l2": "per-step working set ~0.9 GB (U, Q, lattice tables, value buffers) > 126 MB L2: no flush needed",
                       "init_ms": {"set_unary": (t1 - t0) * 1e3, "gaussian_lattice": (t2 - t1) * 1e3,
