@@ -76,8 +76,11 @@ dcrf_status dcrf_set_unary_logistic(dcrf_t* m, const float* Lmat_LxF, int F, con
  * not known to this library). */
 dcrf_status dcrf_set_unary_device(dcrf_t* m, const float* dev_u_LxN);
 /* pydensecrf.utils.unary_from_softmax (utils.py:55-79) fused into the upload: U = -log(clip(scale*p +
- * (1-scale)/L, clip, 1)).  sm: LxN row-major class probabilities; scale <= 0 means "no scale", clip <= 0 "no clip". */
-dcrf_status dcrf_set_unary_from_softmax(dcrf_t* m, const float* sm_LxN, float scale, float clip);
+ * (1-scale)/L, clip, 1)).  sm: LxN row-major class probabilities; scale <= 0 means "no scale", clip <= 0 "no clip".
+ * NumPy's dtype rules are mirrored: with a scale the float32 product scale*p is widened and everything after it is
+ * float64 (the uniform term is a float64 array), without one the clip bounds are float32; the logarithm is taken in
+ * double and rounded once (numpy's float32 log may differ from that by one ulp). */
+dcrf_status dcrf_set_unary_from_softmax(dcrf_t* m, const float* sm_LxN, double scale, double clip);
 
 /* ---- pairwise terms (each builds one permutohedral lattice on the GPU) ------------------------- */
 /* replaces addPairwiseEnergy(c_matrixXf(features), _labelcomp(compat), kernel, normalization)
@@ -144,6 +147,9 @@ dcrf_status dcrf_vec_from_host(const float* data, int n, dcrf_mat_t** out);
 void dcrf_mat_destroy(dcrf_mat_t* a);
 int dcrf_mat_rows(const dcrf_mat_t* a);
 int dcrf_mat_cols(const dcrf_mat_t* a);
+/* 1 while the matrix' current contents live in device memory (results of inference / stepInference that no host view
+ * has claimed), 0 otherwise.  Never allocates. */
+int dcrf_mat_on_device(const dcrf_mat_t* a);
 /* replaces self.m.data() in __getbuffer__             pydensecrf/eigen.pyx:85: pointer to rows*cols floats, col-major
  * (strides (4, 4*rows)), valid until the matrix is destroyed.  Downloads from the device first if the
  * device copy is newer.  The caller may write through it: call dcrf_mat_release_host() when the view
@@ -216,6 +222,10 @@ dcrf_status dcrf_set_iteration_mode(dcrf_t* m, int mode);
  * so Q equals the reference's to the last bit except for rare last-ulp differences in the L%4 tail labels;
  * 1 = fast softmax in the fused kernel: ex2-based exp, tree sum, reciprocal multiply (~1e-6 relative). */
 dcrf_status dcrf_set_softmax_mode(dcrf_t* m, int fast);
+/* Which build of the iteration kernels runs (bit mask; every combination gives identical results): 1 = wide-lane
+ * update kernel (one 256-bit access per lane, csrc/filter_wide.cu), 2 = the update kernel hands Q * diag(norm_k) to the
+ * next iteration's splats.  Default: $DCRF_B200_VARIANT, else 3.  For A/B timing and tests. */
+dcrf_status dcrf_set_kernel_variant(dcrf_t* m, int mask);
 /* MatrixCompatibility::apply (labelcompatibility.cpp:82-84), out = W*Q per pixel:
  * 0 (default) = tcgen05 tensor cores with 3xTF32 split operands from 64 labels up (~1e-6 relative), the exact-order
  *               CUDA-core kernel below that; 1 = always the exact-order kernel (Eigen's GEBP summation order, bit

@@ -447,6 +447,7 @@ typedef struct {
   float *unary;   /* NxL pixel-major, or NULL */
   int nterm;
   orc_term *term;
+  float *pQ; /* the caller-owned Q of the startInference / stepInference protocol (orc_crf_persist_*) */
 } orc_crf;
 
 static float *orc_to_pixel_major(const float *rowmajor, int rows, int cols) {
@@ -479,6 +480,7 @@ void orc_crf_free(void *h) {
   }
   free(m->term);
   free(m->unary);
+  free(m->pQ);
   free(m);
 }
 void orc_crf_set_unary(void *h, const float *u_LxN) {
@@ -701,6 +703,20 @@ void orc_crf_start(void *h, float *Q_NxL) {
 }
 /* DenseCRF::stepInference (:187-201) */
 void orc_crf_step(void *h, float *Q_NxL) { orc_step((orc_crf *)h, Q_NxL, 1); }
+
+/* The stepwise protocol as pydensecrf's wrapper drives it (densecrf.pyx:94-98): Q = startInference() once, then
+   stepInference on the same matrix, no copies in or out.  Used as the timed CPU arm when oracle/_ref is absent. */
+void orc_crf_persist_start(void *h) {
+  orc_crf *m = (orc_crf *)h;
+  free(m->pQ);
+  m->pQ = (float *)malloc(sizeof(float) * ((size_t)m->N * m->L + 4));
+  orc_crf_start(h, m->pQ);
+}
+void orc_crf_persist_step(void *h) { orc_step((orc_crf *)h, ((orc_crf *)h)->pQ, 1); }
+void orc_crf_persist_get(void *h, float *Q_NxL) {
+  orc_crf *m = (orc_crf *)h;
+  memcpy(Q_NxL, m->pQ, sizeof(float) * (size_t)m->N * m->L);
+}
 
 /* DenseCRF::klDivergence (:214-235): float products, double accumulator for the first two terms,
    Eigen's float vectorised sum for each pairwise term. */

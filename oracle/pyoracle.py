@@ -92,6 +92,9 @@ class _Lib:
         self.crf_start = fn("crf_start", None, vp, _fp)
         self.crf_step = fn("crf_step", None, vp, _fp)
         self.crf_kl = fn("crf_kl", C.c_double, vp, _fp)
+        self.crf_persist_start = fn("crf_persist_start", None, vp)
+        self.crf_persist_step = fn("crf_persist_step", None, vp)
+        self.crf_persist_get = fn("crf_persist_get", None, vp, _fp)
         if which == "orc":
             self.lattice_keys = fn("lattice_keys", None, vp, C.POINTER(C.c_short))
             self.crf_term_apply = fn("crf_term_apply", None, vp, C.c_int, _fp, _fp)
@@ -235,6 +238,19 @@ class CRF:
         """stepInference in place on a C-contiguous (N, L) float32 array (no layout copies)."""
         assert q_NxL.flags.c_contiguous and q_NxL.dtype == np.float32 and q_NxL.shape == (self.N, self.L)
         self.lib.crf_step(self.h, _ptr(q_NxL))
+
+    def persist_start(self):
+        """Q, tmp1, tmp2 = startInference() kept inside the checker (no copies): the reference's stepwise protocol."""
+        self.lib.crf_persist_start(self.h)
+
+    def persist_step(self):
+        """stepInference(Q, tmp1, tmp2) on the matrices persist_start created."""
+        self.lib.crf_persist_step(self.h)
+
+    def persist_q(self):
+        q = self._q()
+        self.lib.crf_persist_get(self.h, _ptr(q))
+        return q.T
 
     def klDivergence(self, Q):
         q = np.ascontiguousarray(Q.T, dtype=np.float32)

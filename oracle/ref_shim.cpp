@@ -56,6 +56,7 @@ struct Model {
   DenseCRF* crf;
   DenseCRF2D* crf2d;
   int N, L;
+  MatrixXf Q, t1, t2;  // the caller-owned matrices of the startInference / stepInference protocol (densecrf.pyx:94-98)
 };
 }  // namespace
 
@@ -161,6 +162,22 @@ void ref_crf_step(void* h, float* Q_NxL) {
   MatrixXf Q = Eigen::Map<const MatrixXf>(Q_NxL, m->L, m->N), t1, t2;
   m->crf->stepInference(Q, t1, t2);
   std::memcpy(Q_NxL, Q.data(), sizeof(float) * (size_t)m->L * m->N);
+}
+// The reference's stepwise protocol exactly as its Python wrapper drives it: Q, tmp1, tmp2 = startInference() once, then
+// stepInference(Q, tmp1, tmp2) on the same three matrices -- no copies in or out (used as the timed CPU arm).
+void ref_crf_persist_start(void* h) {
+  Model* m = static_cast<Model*>(h);
+  m->Q = m->crf->startInference();
+  m->t1 = MatrixXf();
+  m->t2 = MatrixXf();
+}
+void ref_crf_persist_step(void* h) {
+  Model* m = static_cast<Model*>(h);
+  m->crf->stepInference(m->Q, m->t1, m->t2);
+}
+void ref_crf_persist_get(void* h, float* Q_NxL) {
+  Model* m = static_cast<Model*>(h);
+  std::memcpy(Q_NxL, m->Q.data(), sizeof(float) * (size_t)m->L * m->N);
 }
 double ref_crf_kl(void* h, const float* Q_NxL) {
   Model* m = static_cast<Model*>(h);

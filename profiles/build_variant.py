@@ -1,5 +1,5 @@
 """Build a variant of libdcrf_b200.so with extra -D flags into build/variants/<name>/ for A/B timing on the GPU box:
-  [VARIANT_SRC=filter,matrix_tc] python profiles/build_variant.py <name> [-DFOO=1 ...]   (sources rebuilt with the flags; default filter)
+  [VARIANT_SRC=filter,filter_wide] python profiles/build_variant.py <name> [-DFOO=1 ...]   (sources rebuilt with the flags)
   LD_LIBRARY_PATH=build/variants/<name> python profiles/quick_bench.py <name>
 (the binding finds the library through LD_LIBRARY_PATH before its RUNPATH)."""
 import os, subprocess, sys
@@ -10,9 +10,9 @@ name, defs = sys.argv[1], sys.argv[2:]
 out = os.path.join(ROOT, "build", "variants", name)
 os.makedirs(out, exist_ok=True)
 objs = []
-for n in ("lattice", "filter", "matrix_tc", "api"):
+for n in ("lattice", "filter", "filter_wide", "matrix_tc", "api"):
     src, obj = os.path.join(g.CSRC, n + ".cu"), os.path.join(out, n + ".o")
-    if n in os.environ.get("VARIANT_SRC", "filter").split(",") or not defs:
+    if n in os.environ.get("VARIANT_SRC", "filter,filter_wide").split(",") and defs:
         subprocess.check_call(["nvcc"] + g.NVCC_FLAGS + defs + ["-c", src, "-o", obj])
     else:
         obj = os.path.join(g.BUILD, n + ".o")

@@ -32,7 +32,7 @@ cdef extern from "dcrf_b200.h" nogil:
     void dcrf_destroy(dcrf_t* m)
     int dcrf_set_unary_const(dcrf_t* m, const float* u)
     int dcrf_set_unary_logistic(dcrf_t* m, const float* Lmat, int F, const float* f)
-    int dcrf_set_unary_from_softmax(dcrf_t* m, const float* sm, float scale, float clip)
+    int dcrf_set_unary_from_softmax(dcrf_t* m, const float* sm, double scale, double clip)
     int dcrf_set_unary_device(dcrf_t* m, const float* dev_u)
     int dcrf_mat_device_ptr(dcrf_mat_t* a, float** ptr, int* pitch, int* device)
     int dcrf_add_pairwise_nd(dcrf_t* m, int nsp, const int* dims, const float* sdims, int nch, const float* schan,
@@ -53,6 +53,7 @@ cdef extern from "dcrf_b200.h" nogil:
     void dcrf_mat_destroy(dcrf_mat_t* a)
     int dcrf_mat_rows(const dcrf_mat_t* a)
     int dcrf_mat_cols(const dcrf_mat_t* a)
+    int dcrf_mat_on_device(const dcrf_mat_t* a)
     int dcrf_mat_host_ptr(dcrf_mat_t* a, float** ptr)
     void dcrf_mat_release_host(dcrf_mat_t* a)
     int dcrf_synchronize(dcrf_t* m)
@@ -75,6 +76,7 @@ cdef extern from "dcrf_b200.h" nogil:
     int dcrf_pairwise_apply(dcrf_t* m, int k, dcrf_mat_t* Q, dcrf_mat_t** out)
     int dcrf_set_iteration_mode(dcrf_t* m, int mode)
     int dcrf_set_softmax_mode(dcrf_t* m, int fast)
+    int dcrf_set_kernel_variant(dcrf_t* m, int mask)
     int dcrf_set_matrix_mode(dcrf_t* m, int mode)
     int dcrf_host_alloc(size_t nbytes, void** out)
     void dcrf_host_free(void* p, size_t nbytes)
@@ -337,7 +339,11 @@ cdef class MatrixXf:
         while the current contents live on the GPU (i.e. for results of inference / stepInference)."""
         cdef float* p = NULL
         cdef int pitch = 0, dev = 0
-        _check(dcrf_mat_device_ptr(self.handle(), &p, &pitch, &dev))
+        # hasattr() probes (cupy.asarray, numba, ...) only swallow AttributeError: a host-resident matrix has no such
+        # attribute, and probing must not allocate anything
+        if self.h == NULL or not dcrf_mat_on_device(self.h):
+            raise AttributeError("__cuda_array_interface__: the matrix' current contents are on the host")
+        _check(dcrf_mat_device_ptr(self.h, &p, &pitch, &dev))
         self._refresh()
         return {"shape": (self.shape[1], self.shape[0]), "typestr": "<f4", "data": (<size_t>p, False),
                 "strides": (pitch * 4, 4), "version": 3}
@@ -624,8 +630,8 @@ cdef class DenseCRF:
         if scale is not None and not (0 < scale <= 1):
             raise ValueError("`scale` needs to be in (0,1]")
         cdef float[:, ::1] v = a
-        cdef float sc = -1.0 if scale is None else scale
-        cdef float cl = -1.0 if clip is None else clip
+        cdef double sc = -1.0 if scale is None else scale
+        cdef double cl = -1.0 if clip is None else clip
         cdef int st
         with nogil:
             st = dcrf_set_unary_from_softmax(self._h, &v[0, 0], sc, cl)
@@ -765,6 +771,10 @@ cdef class DenseCRF:
     def setSoftmaxMode(self, bint fast):
         """False (default): bit-faithful softmax; True: faster approximate softmax (~1e-6 relative)."""
         _check(dcrf_set_softmax_mode(self._h, 1 if fast else 0))
+
+    def _set_kernel_variant(self, int mask):
+        """Bit mask: 1 wide-lane update kernel, 2 pre-scaled Q copies for the splats.  Identical results; for A/B timing."""
+        _check(dcrf_set_kernel_variant(self._h, mask))
 
     def setMatrixCompatMode(self, int mode):
         """0 (default): tensor cores (3xTF32) for MatrixCompatibility from 64 labels up; 1: always the

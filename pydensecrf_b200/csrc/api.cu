@@ -220,6 +220,7 @@ struct Term {
   float *Whi = nullptr, *Wlo = nullptr;  // tf32 split of Wm, zero padded (tensor-core path)
   float *valA = nullptr, *valB = nullptr;  // (V+1) x Lp ping-pong value buffers (one allocation)
   float* msg = nullptr;                    // N x Lp message of this term (tensor-core update path only)
+  float* qn = nullptr;                     // N x Lp: Q * diag(norm), written by the update kernel for this term's next splat
   size_t val_bytes = 0;
   bool pre() const { return ntype == DCRF_NORMALIZE_SYMMETRIC || ntype == DCRF_NORMALIZE_BEFORE; }
   bool post() const { return ntype == DCRF_NORMALIZE_SYMMETRIC || ntype == DCRF_NORMALIZE_AFTER; }
@@ -237,6 +238,7 @@ struct dcrf_model {
   double* kl_sums = nullptr;
   int iter_mode = 0;
   bool fast_softmax = false;
+  int variant = 0;      // kernel variants, see default_variant()
   int matrix_mode = 0;  // 0: tensor cores from 64 labels up, 1: always the exact-order kernel, 2: tensor cores whenever possible
   cudaEvent_t t0 = nullptr, t1 = nullptr;
   char* flush_buf = nullptr;
@@ -265,6 +267,18 @@ struct dcrf_model {
 };
 
 namespace {
+
+// Kernel variants (bit mask; every combination gives identical bits).  1: wide-lane update kernel (filter_wide.cu);
+// 2: the update kernel also writes Q * diag(norm_k) for every pre-normalised term and the next splat reads that copy
+// instead of Q and norm.  $DCRF_B200_VARIANT / dcrf_set_kernel_variant choose for A/B timing and tests.
+enum { VAR_WIDE_UPDATE = 1, VAR_PRESCALED_Q = 2, VAR_ALL = 3 };
+int default_variant() {
+  static const int v = [] {
+    const char* e = std::getenv("DCRF_B200_VARIANT");
+    return e ? (std::atoi(e) & VAR_ALL) : VAR_ALL;
+  }();
+  return v;
+}
 
 template <typename F>
 dcrf_status guarded(F&& f) {
@@ -314,13 +328,14 @@ dcrf_model* model_new(int N, int L, int W, int H, int device) {
   DCRF_CUDA(cudaEventCreate(&m->t1));
   m->kl_sums = dev_alloc<double>(3, m->stream);
   m->use_graphs = std::getenv("DCRF_B200_NO_GRAPHS") == nullptr;
+  m->variant = default_variant();
   return m;
 }
 
 void term_free(dcrf_model* m, Term* t) {
   cudaStream_t s = m->stream;
   if (!t->shared) t->lat.release(s);
-  for (void* p : {(void*)t->norm, (void*)t->diag, (void*)t->Wm, (void*)t->Whi, (void*)t->Wlo, (void*)t->valA, (void*)t->msg})
+  for (void* p : {(void*)t->norm, (void*)t->diag, (void*)t->Wm, (void*)t->Whi, (void*)t->Wlo, (void*)t->valA, (void*)t->msg, (void*)t->qn})
     dev_free(p, s);
   delete t;
 }
@@ -359,16 +374,13 @@ const float* run_filter(Ctx cx, const Lattice& lt, RowLayout rl, const float* in
   for (int i = 0; i < n; i++) {
     const int j = reverse ? n - 1 - i : i;
     const int j2 = reverse ? j - 1 : j + 1;  // the axis after j in blur order
-    if (rl.C <= 32 && lt.nchains[j] > 0) {
-      launch_blur_chain(cx, lt, rl, j, src);  // in place
-    } else if (pair_blur && i + 1 < n && lt.nchains[j2] == 0 && lt.V >= pair_blur) {
+    if (pair_blur && i + 1 < n && lt.V >= pair_blur) {
       launch_blur2(cx, lt, rl, j, j2, src, dst);  // axes j and j2 together
-      std::swap(src, dst);
       i++;
     } else {
       launch_blur(cx, lt, rl, j, src, dst);
-      std::swap(src, dst);
     }
+    std::swap(src, dst);
   }
   return src;
 }
@@ -433,7 +445,7 @@ void ensure_aux(dcrf_model* m, int nterms) {
 // every term's filter (splat + blurs) for the current Q; term k > 0 runs on its own side stream next to term 0 and
 // joins the main stream again before returning.  vals[k] = the buffer holding term k's blurred vertex values.
 // slice_msgs: also slice + post-normalise each term into its own message array (Term::msg) on the same stream.
-void filter_all_terms(dcrf_model* m, const float* Q, const float** vals, bool slice_msgs = false) {
+void filter_all_terms(dcrf_model* m, const float* Q, const float** vals, bool slice_msgs = false, bool prescaled = false) {
   Ctx cx = m->cx();
   const int nterms = (int)m->terms.size();
   for (int k = 0; k < nterms; k++) ensure_val(m, m->terms[k]);
@@ -455,7 +467,9 @@ void filter_all_terms(dcrf_model* m, const float* Q, const float** vals, bool sl
       ck.stream = m->aux[k - 1];
       DCRF_CUDA(cudaStreamWaitEvent(ck.stream, m->fork, 0));
     }
-    vals[k] = run_filter(ck, t->lat, m->rl, Q, t->pre() ? t->norm : nullptr, t->valA, t->valB);
+    // prescaled: the previous update kernel left Q * diag(norm) in t->qn (bit-identical to scaling in the splat)
+    const bool pre_done = prescaled && t->pre() && t->qn;
+    vals[k] = run_filter(ck, t->lat, m->rl, pre_done ? t->qn : Q, (t->pre() && !pre_done) ? t->norm : nullptr, t->valA, t->valB);
     if (slice_msgs) {
       ensure_msg(m, t);
       launch_slice(ck, t->lat, m->rl, vals[k], t->post() ? t->norm : nullptr, nullptr, SLICE_WRITE, nullptr, false, t->msg);
@@ -476,10 +490,44 @@ bool can_tc_update(dcrf_model* m) {
   return update_matrix_tc_supported(m->rl, (int)m->terms.size());
 }
 
-// one mean-field update of Q in place (the loop body of densecrf.cpp:122-129 / :187-200)
-void mf_step(dcrf_model* m, float* Q, bool neg_unary) {
+bool fuse_wanted(dcrf_model* m) { return m->iter_mode == 2 || (m->iter_mode == 0 && can_fuse(m)); }
+// inference(n) with the fused kernel and at least one pre-normalised term: the iterations hand Q * diag(norm) on
+bool prescale_wanted(dcrf_model* m) {
+  if (!(m->variant & VAR_PRESCALED_Q) || !fuse_wanted(m) || !can_fuse(m)) return false;
+  for (Term* t : m->terms)
+    if (t->pre()) return true;
+  return false;
+}
+void ensure_qn(dcrf_model* m) {
+  for (Term* t : m->terms)
+    if (t->pre() && !t->qn) t->qn = dev_alloc<float>((size_t)m->N * m->rl.Lp, m->stream);
+}
+// which copies of the new Q does an update kernel have to store?  qn_out: the next iteration's splats read the pre-scaled
+// copies; Q itself is then only needed by terms without a pre-normalisation (or by the caller: keep_q)
+void set_outputs(dcrf_model* m, FusedArgs& a, bool qn_out, bool keep_q) {
+  a.nqn = 0;
+  bool q_needed = keep_q || !qn_out;
+  if (qn_out)
+    for (Term* t : m->terms) {
+      if (t->pre() && t->qn) {
+        a.qn[a.nqn] = t->qn, a.qn_norm[a.nqn] = t->norm;
+        a.nqn++;
+      } else {
+        q_needed = true;
+      }
+    }
+  a.write_q = q_needed ? 1 : 0;
+}
+void run_fused(dcrf_model* m, const FusedArgs& a) {
+  if (m->fast_softmax || !(m->variant & VAR_WIDE_UPDATE) || !launch_fused_update8(m->cx(), m->rl, a))
+    launch_fused_update(m->cx(), m->rl, a, m->fast_softmax);
+}
+
+// one mean-field update of Q in place (the loop body of densecrf.cpp:122-129 / :187-200).  qn_in: the terms' pre-scaled
+// copies of Q are current (written by the previous update of the same inference call); qn_out / keep_q: see set_outputs.
+void mf_step(dcrf_model* m, float* Q, bool neg_unary, bool qn_in = false, bool qn_out = false, bool keep_q = true) {
   Ctx cx = m->cx();
-  const bool fuse = m->iter_mode == 2 || (m->iter_mode == 0 && can_fuse(m));
+  const bool fuse = fuse_wanted(m);
   const float* vals[std::max(kMaxFusedTerms, kMaxTCUTerms)];
   if (fuse) {
     DCRF_REQUIRE(can_fuse(m), "fused iteration not available for this model (matrix compatibility, >128 labels or >8 terms)");
@@ -490,7 +538,7 @@ void mf_step(dcrf_model* m, float* Q, bool neg_unary) {
     a.U = m->U;
     a.neg_unary = neg_unary ? 1 : 0;
     a.Q = Q;
-    filter_all_terms(m, Q, vals);
+    filter_all_terms(m, Q, vals, false, qn_in);
     for (int k = 0; k < a.nterms; k++) {
       Term* t = m->terms[k];
       FusedTerm& ft = a.t[k];
@@ -503,7 +551,8 @@ void mf_step(dcrf_model* m, float* Q, bool neg_unary) {
       ft.dp1 = t->lat.d + 1;
       ft.ckind = t->ckind;
     }
-    launch_fused_update(cx, m->rl, a, m->fast_softmax);
+    set_outputs(m, a, qn_out, keep_q);
+    run_fused(m, a);
   } else if (can_tc_update(m)) {
     TCUArgs a;
     a.N = m->N;
@@ -541,16 +590,27 @@ void ensure_scratch_if_staged(dcrf_model* m) {
 }
 
 // Q0 = expAndNormalize(-unary) (densecrf.cpp:120)
-void mf_init(dcrf_model* m, float* Q) {
+void mf_init(dcrf_model* m, float* Q, bool qn_out = false, bool keep_q = true) {
   Ctx cx = m->cx();
   if (m->iter_mode != 1 && fused_update_supported(m->rl) && (uint64_t)m->N * m->rl.Lp < (1ull << 31)) {
     FusedArgs a;
     a.N = m->N, a.W = m->W, a.H = m->H, a.nterms = 0, a.U = m->U, a.neg_unary = 1, a.Q = Q;
-    launch_fused_update(cx, m->rl, a, m->fast_softmax);
+    set_outputs(m, a, qn_out, keep_q);
+    run_fused(m, a);
   } else {
     ensure_scratch(m);
     launch_init_acc(cx, m->rl, m->N, m->U, true, m->acc);
     launch_softmax(cx, m->rl, m->N, m->acc, Q);
+  }
+}
+
+// inference(n): Q0, then n updates.  With pre-scaled copies the inner iterations never store Q itself.
+void mf_run(dcrf_model* m, float* q, int n_iterations) {
+  const bool ps = n_iterations > 0 && prescale_wanted(m);
+  mf_init(m, q, ps, !ps);
+  for (int it = 0; it < n_iterations; it++) {
+    const bool last = it + 1 == n_iterations;
+    mf_step(m, q, true, ps, ps && !last, last);
   }
 }
 
@@ -580,7 +640,10 @@ float* mat_device(dcrf_model* m, dcrf_mat* a, bool need_contents) {
     a->device = m->device;
     a->dev_valid = false;
   }
-  if (!a->ready) DCRF_CUDA(cudaEventCreateWithFlags(&a->ready, cudaEventDisableTiming));
+  if (!a->ready)
+    DCRF_CUDA(cudaEventCreateWithFlags(&a->ready, cudaEventDisableTiming));
+  else if (a->dev)  // another model's stream may have produced or may still be reading the buffer: order after it
+    DCRF_CUDA(cudaStreamWaitEvent(m->stream, a->ready, 0));
   if (need_contents && !a->dev_valid) {
     DCRF_REQUIRE(a->host && a->host_valid, "matrix has no contents");
     float* stage = dev_alloc<float>((size_t)m->N * m->L, m->stream);
@@ -953,10 +1016,10 @@ dcrf_status dcrf_set_unary_device(dcrf_t* m, const float* dev_u_LxN) {
     DCRF_CUDA(cudaStreamSynchronize(m->stream));  // the caller may reuse its buffer now
   });
 }
-dcrf_status dcrf_set_unary_from_softmax(dcrf_t* m, const float* sm_LxN, float scale, float clip) {
+dcrf_status dcrf_set_unary_from_softmax(dcrf_t* m, const float* sm_LxN, double scale, double clip) {
   return guarded([&] {
     DCRF_REQUIRE(m && sm_LxN, "null argument");
-    DCRF_REQUIRE(!(scale > 1.f), "`scale` needs to be in (0,1]");
+    DCRF_REQUIRE(!(scale > 1.0), "`scale` needs to be in (0,1]");
     DeviceGuard g(m->device);
     const size_t n = (size_t)m->N * m->L;
     float* planes = upload_tmp(m, sm_LxN, n * sizeof(float));
@@ -1093,6 +1156,7 @@ dcrf_status dcrf_inference_into(dcrf_t* m, int n_iterations, dcrf_mat_t* Q) {
     // everything the launches need is allocated up front, so the sequence below is capturable
     for (Term* t : m->terms) ensure_val(m, t);
     ensure_scratch_if_staged(m);
+    if (n_iterations > 0 && prescale_wanted(m)) ensure_qn(m);
     ensure_aux(m, (int)m->terms.size());
     if (m->use_graphs && !m->prof.enabled && n_iterations > 0) {
       dcrf_model::GraphEntry* hit = nullptr;
@@ -1103,22 +1167,19 @@ dcrf_status dcrf_inference_into(dcrf_t* m, int n_iterations, dcrf_mat_t* Q) {
         // graph costs more than it saves for one-shot models (a fresh model per image, cfg 4)
         if (m->graphs.size() >= 8) m->drop_graphs();
         m->graphs.push_back({q, n_iterations, nullptr, 0});
-        mf_init(m, q);
-        for (int it = 0; it < n_iterations; it++) mf_step(m, q, true);
+        mf_run(m, q, n_iterations);
       } else if (!hit->exec && hit->direct_runs < 2) {
         // second call: still direct -- capturing and instantiating costs several milliseconds, which only a caller
         // who keeps repeating the same inference earns back
         hit->direct_runs++;
-        mf_init(m, q);
-        for (int it = 0; it < n_iterations; it++) mf_step(m, q, true);
+        mf_run(m, q, n_iterations);
       } else {
         if (!hit->exec) {  // third call: capture the launch sequence (side streams included) once
           const int64_t l0 = m->prof.launches;
           cudaGraph_t graph = nullptr;
           DCRF_CUDA(cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal));
           try {
-            mf_init(m, q);
-            for (int it = 0; it < n_iterations; it++) mf_step(m, q, true);
+            mf_run(m, q, n_iterations);
           } catch (...) {
             cudaStreamEndCapture(m->stream, &graph);
             if (graph) cudaGraphDestroy(graph);
@@ -1137,8 +1198,7 @@ dcrf_status dcrf_inference_into(dcrf_t* m, int n_iterations, dcrf_mat_t* Q) {
         m->prof.launches += hit->launches;
       }
     } else {
-      mf_init(m, q);
-      for (int it = 0; it < n_iterations; it++) mf_step(m, q, true);
+      mf_run(m, q, n_iterations);
     }
     DCRF_CUDA(cudaGetLastError());
     mat_written(m, Q);
@@ -1221,6 +1281,7 @@ dcrf_status dcrf_current_map(dcrf_t* m, dcrf_mat_t* Q, int16_t* labels_N) {
     float* q = mat_device(m, Q, true);
     int16_t* d = dev_alloc<int16_t>(m->N, m->stream);
     launch_argmax(m->cx(), m->rl, m->N, q, d);
+    DCRF_CUDA(cudaEventRecord(Q->ready, m->stream));  // a later writer on another stream has to wait for this read
     DCRF_CUDA(cudaMemcpyAsync(labels_N, d, (size_t)m->N * sizeof(int16_t), cudaMemcpyDeviceToHost, m->stream));
     dev_free(d, m->stream);
     DCRF_CUDA(cudaStreamSynchronize(m->stream));
@@ -1262,6 +1323,7 @@ void dcrf_mat_destroy(dcrf_mat_t* a) {
 }
 int dcrf_mat_rows(const dcrf_mat_t* a) { return a ? a->rows : 0; }
 int dcrf_mat_cols(const dcrf_mat_t* a) { return a ? a->cols : 0; }
+int dcrf_mat_on_device(const dcrf_mat_t* a) { return (a && a->dev && a->dev_valid) ? 1 : 0; }
 dcrf_status dcrf_mat_host_ptr(dcrf_mat_t* a, float** ptr) {
   return guarded([&] {
     DCRF_REQUIRE(a && ptr, "null argument");
@@ -1285,6 +1347,9 @@ dcrf_status dcrf_mat_host_ptr(dcrf_mat_t* a, float** ptr) {
       a->host_valid = true;
     }
     a->exports++;
+    // the view is writable (readonly=0, eigen.pyx:40,92) and shares memory with the matrix in the reference: while it
+    // is alive the host copy is the authoritative one, so the next device consumer uploads it again
+    a->dev_valid = false;
     *ptr = a->host;
   });
 }
@@ -1598,6 +1663,13 @@ dcrf_status dcrf_set_matrix_mode(dcrf_t* m, int mode) {
   return guarded([&] {
     DCRF_REQUIRE(m && mode >= 0 && mode <= 2, "bad matrix compatibility mode");
     m->matrix_mode = mode;
+    m->drop_graphs();
+  });
+}
+dcrf_status dcrf_set_kernel_variant(dcrf_t* m, int mask) {
+  return guarded([&] {
+    DCRF_REQUIRE(m && mask >= 0 && mask <= VAR_ALL, "bad kernel variant mask");
+    m->variant = mask;
     m->drop_graphs();
   });
 }

@@ -148,12 +148,6 @@ struct Lattice {
   CsrEntry* csr = nullptr;     // [E]
   int2* nbr = nullptr;         // [(d+1)*V] rows (id+1) of the -/+ neighbours, 0 = absent
   int* order = nullptr;        // [V] splat work order: windows of 4096 vertex ids, inside a window by CSR row length
-  // blur chains: along axis j the vertices form disjoint paths v -> n+(v) -> ...; a path that is walked by one
-  // thread group can be blurred IN PLACE (one read + one write per vertex instead of three reads + one write)
-  int* chain_vid = nullptr;    // [(d+1)*V] vertex ids, path by path, per axis
-  int* chain_start = nullptr;  // per axis nchains+1 prefix offsets into that axis' V entries
-  std::vector<int> nchains;    // per axis; 0 = axis not eligible (paths too long / too few): ping-pong blur
-  std::vector<size_t> chain_off;  // per axis offset into chain_start
   int16_t* keys = nullptr;     // [V*d]
   float alpha = 1.f;           // 1/(1+2^-d)
   int max_row = 0;             // longest CSR row (diagnostic)
@@ -172,8 +166,6 @@ void launch_splat(Ctx cx, const Lattice& lt, RowLayout rl, const float* in, cons
 void launch_blur(Ctx cx, const Lattice& lt, RowLayout rl, int axis, const float* src, float* dst);
 // axis `axis` then axis `axis2` in one launch (bit-identical to two launch_blur calls)
 void launch_blur2(Ctx cx, const Lattice& lt, RowLayout rl, int axis, int axis2, const float* src, float* dst);
-// in-place variant over the axis' chains (only when lt.nchains[axis] > 0)
-void launch_blur_chain(Ctx cx, const Lattice& lt, RowLayout rl, int axis, float* val);
 
 enum SliceMode { SLICE_WRITE = 0, SLICE_ACC_FIRST = 1, SLICE_ACC_NEXT = 2 };
 struct CompatDev {
@@ -206,6 +198,12 @@ struct FusedArgs {
   int neg_unary;   // 1: start from -U (inference), 0: start from 0-U (stepInference)
   float* Q;
   float c_one, c_nzero, c_mone;  // 1, -0, -1: filled in by launch_fused_update (opaque operands of the packed kernel)
+  // Pre-scaled copies of the new Q for the next iteration's splats: qn[j][i] = Q[i] * qn_norm[j][i], the product
+  // DenseKernel::filter forms first (pairwise.cpp:65-66), computed once per pixel here instead of once per
+  // contribution in the splat.  write_q = 0 skips storing Q itself (an inner iteration nobody reads Q of).
+  int write_q = 1, nqn = 0;
+  float* qn[kMaxFusedTerms];
+  const float* qn_norm[kMaxFusedTerms];
   FusedTerm t[kMaxFusedTerms];
 };
 // arithmetic self-tests (see k_selftest); *bad (device) receives the number of mismatching elements
@@ -213,6 +211,8 @@ void launch_selftest(Ctx cx, int which, unsigned long long n, unsigned long long
 bool fused_update_supported(RowLayout rl);
 // Q = softmax_col( -U - sum_k compat_k(norm_k * slice_k) ), everything in one pass
 void launch_fused_update(Ctx cx, RowLayout rl, const FusedArgs& a, bool fast);
+// wide-lane build of the same kernel; false = no instantiation for this shape (take launch_fused_update)
+bool launch_fused_update8(Ctx cx, RowLayout rl, const FusedArgs& a);
 // Q = softmax_col(acc) for any L (staged path)
 void launch_softmax(Ctx cx, RowLayout rl, int N, const float* acc, float* Q);
 // acc = -U / 0-U / -0 (no terms at all)
@@ -248,7 +248,7 @@ void launch_matrix_compat_tc(Ctx cx, RowLayout rl, int N, const float* Bhi, cons
 // layout conversion at the boundary
 void launch_planes_to_rows(Ctx cx, RowLayout rl, int N, const float* planes_LxN, float* rows_NxLp);
 // same transposition with utils.unary_from_softmax (utils.py:55-79) applied on the way: -log(clip(scale*p + (1-scale)/L))
-void launch_softmax_planes_to_unary(Ctx cx, RowLayout rl, int N, const float* planes_LxN, float scale, float clip,
+void launch_softmax_planes_to_unary(Ctx cx, RowLayout rl, int N, const float* planes_LxN, double scale, double clip,
                                     float* rows_NxLp);
 void launch_unpack_rows(Ctx cx, RowLayout rl, int N, const float* packed_NxL, float* rows_NxLp);
 void launch_pack_rows(Ctx cx, RowLayout rl, int N, const float* rows_NxLp, float* packed_NxL);

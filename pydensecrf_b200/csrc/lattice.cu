@@ -319,51 +319,6 @@ __global__ void k_order_keys(int V, const int* __restrict__ count, uint32_t* __r
   val[v] = (uint32_t)v;
 }
 
-// ---- blur chains ---------------------------------------------------------------------------------------
-__global__ void k_chain_flag(int V, const int2* __restrict__ nbr, int* __restrict__ flag) {
-  const int v = blockIdx.x * blockDim.x + threadIdx.x;
-  if (v < V) flag[v] = (nbr[v].x == 0) ? 1 : 0;  // no predecessor along this axis: head of a path
-}
-__global__ void k_chain_heads(int V, const int* __restrict__ flag, const int* __restrict__ pos, int* __restrict__ heads) {
-  const int v = blockIdx.x * blockDim.x + threadIdx.x;
-  if (v < V && flag[v]) heads[pos[v]] = v;
-}
-constexpr int kMaxChainLen = 255;
-__global__ void k_chain_len(int nh, const int* __restrict__ heads, const int2* __restrict__ nbr, uint32_t* __restrict__ key,
-                            uint32_t* __restrict__ val, int* __restrict__ too_long) {
-  const int h = blockIdx.x * blockDim.x + threadIdx.x;
-  if (h >= nh) return;
-  int v = heads[h], len = 1;
-  for (;;) {
-    const int nx = nbr[v].y;  // row of the successor (id + 1), 0 = none
-    if (nx == 0) break;
-    v = nx - 1;
-    if (++len > kMaxChainLen) {
-      atomicExch(too_long, 1);
-      break;
-    }
-  }
-  key[h] = ((uint32_t)(heads[h] >> 12) << 8) | (uint32_t)min(len, 255);  // coarse locality, then equal lengths together
-  val[h] = ((uint32_t)h);
-}
-__global__ void k_chain_lens_sorted(int nh, const uint32_t* __restrict__ key_sorted, int* __restrict__ len) {
-  const int h = blockIdx.x * blockDim.x + threadIdx.x;
-  if (h < nh) len[h] = (int)(key_sorted[h] & 255u);
-  if (h == nh) len[h] = 0;
-}
-__global__ void k_chain_fill(int nh, const uint32_t* __restrict__ order, const int* __restrict__ heads,
-                             const int* __restrict__ start, const int2* __restrict__ nbr, int* __restrict__ chain_vid) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= nh) return;
-  int v = heads[order[c]];
-  int o = start[c];
-  const int e = start[c + 1];
-  for (; o < e; o++) {
-    chain_vid[o] = v;
-    v = nbr[v].y - 1;
-  }
-}
-
 __global__ void k_max_int(int n, const int* __restrict__ a, int* __restrict__ out) {
   int m = 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = max(m, a[i]);
@@ -523,69 +478,6 @@ void build_impl(Ctx cx, const ElevateParams& ep, Lattice* L) {
     dim3 grid(blocks_for(V), dp1);
     k_neighbours<D><<<grid, kThreads, 0, s>>>(V, d, L->keys, table, (uint32_t)(cap - 1), L->nbr);
   }
-  // blur chains per axis (see Lattice::chain_vid)
-  L->nchains.assign(dp1, 0);
-  L->chain_off.assign(dp1, 0);
-  // Measured on B200 (profiles/r01f_chain_blur.txt): the in-place walk halves the row accesses but the 82 MB
-  // bilateral buffer still does not stay in L2 between passes and the walk is latency bound, so it is no faster
-  // than the ping-pong kernel (40 vs 37 us per pass).  Off unless $DCRF_B200_CHAIN_MIN asks for it.
-  static const int min_chains = [] {
-    const char* e = std::getenv("DCRF_B200_CHAIN_MIN");
-    return e ? std::atoi(e) : 0;
-  }();
-  if (V > 0 && min_chains > 0) {
-    LaunchScope ls(cx.prof, s, "lattice_chains");
-    L->chain_vid = dev_alloc<int>((size_t)dp1 * V, s);
-    L->chain_start = dev_alloc<int>((size_t)dp1 * ((size_t)V + 1), s);
-    int* cflag = dev_alloc<int>((size_t)V + 1, s);
-    int* cpos = dev_alloc<int>((size_t)V + 1, s);
-    int* heads = dev_alloc<int>(V, s);
-    int* clen = dev_alloc<int>((size_t)V + 1, s);
-    uint32_t* ck = dev_alloc<uint32_t>(V, s);
-    uint32_t* ck2 = dev_alloc<uint32_t>(V, s);
-    uint32_t* cv = dev_alloc<uint32_t>(V, s);
-    uint32_t* cv2 = dev_alloc<uint32_t>(V, s);
-    int* dflag = dev_alloc<int>(1, s);
-    size_t scan_bytes = 0, sort_bytes = 0;
-    DCRF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, cflag, cpos, V + 1, s));
-    int kbits = 9;
-    while ((1ull << (kbits - 8)) <= ((uint64_t)V >> 12)) kbits++;
-    DCRF_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, ck, ck2, cv, cv2, V, 0, kbits, s));
-    void* tmp = dev_alloc<char>(std::max(scan_bytes, sort_bytes), s);
-    size_t off = 0;
-    for (int j = 0; j < dp1; j++) {
-      const int2* nb = L->nbr + (size_t)j * V;
-      DCRF_CUDA(cudaMemsetAsync(cflag + V, 0, sizeof(int), s));
-      k_chain_flag<<<blocks_for(V), kThreads, 0, s>>>(V, nb, cflag);
-      size_t tb = scan_bytes;
-      DCRF_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, cflag, cpos, V + 1, s));
-      int nh = 0;
-      DCRF_CUDA(cudaMemcpyAsync(&nh, cpos + V, sizeof(int), cudaMemcpyDeviceToHost, s));
-      DCRF_CUDA(cudaStreamSynchronize(s));
-      // worth it only when there are enough independent paths to fill the GPU
-      if (nh < min_chains) continue;
-      k_chain_heads<<<blocks_for(V), kThreads, 0, s>>>(V, cflag, cpos, heads);
-      DCRF_CUDA(cudaMemsetAsync(dflag, 0, sizeof(int), s));
-      k_chain_len<<<blocks_for(nh), kThreads, 0, s>>>(nh, heads, nb, ck, cv, dflag);
-      int too_long = 0;
-      DCRF_CUDA(cudaMemcpyAsync(&too_long, dflag, sizeof(int), cudaMemcpyDeviceToHost, s));
-      DCRF_CUDA(cudaStreamSynchronize(s));
-      if (too_long) continue;
-      tb = sort_bytes;
-      DCRF_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, ck, ck2, cv, cv2, nh, 0, kbits, s));
-      k_chain_lens_sorted<<<blocks_for(nh + 1), kThreads, 0, s>>>(nh, ck2, clen);
-      int* cstart = L->chain_start + off;
-      tb = scan_bytes;
-      DCRF_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, clen, cstart, nh + 1, s));
-      k_chain_fill<<<blocks_for(nh), kThreads, 0, s>>>(nh, cv2, heads, cstart, nb, L->chain_vid + (size_t)j * V);
-      L->nchains[j] = nh;
-      L->chain_off[j] = off;
-      off += (size_t)nh + 1;
-    }
-    for (void* q : {(void*)cflag, (void*)cpos, (void*)heads, (void*)clen, (void*)ck, (void*)ck2, (void*)cv, (void*)cv2,
-                    (void*)dflag, (void*)tmp})
-      dev_free(q, s);
-  }
   int* dmax = dev_alloc<int>(1, s);
   DCRF_CUDA(cudaMemsetAsync(dmax, 0, sizeof(int), s));
   if (V > 0) k_max_int<<<128, kThreads, 0, s>>>(V, count, dmax);
@@ -607,11 +499,7 @@ void Lattice::release(cudaStream_t s) {
   dev_free(nbr, s);
   dev_free(keys, s);
   dev_free(order, s);
-  dev_free(chain_vid, s);
-  dev_free(chain_start, s);
   order = nullptr;
-  chain_vid = nullptr;
-  chain_start = nullptr;
   pix = nullptr;
   csr_start = nullptr;
   csr = nullptr;
