@@ -120,6 +120,9 @@ dcrf_status dcrf_kl_divergence(dcrf_t* m, dcrf_mat_t* Q, double* out);
 /* DenseCRF::currentMap (densecrf.cpp:202-211; unwrapped in the reference's .pyx:61-62):
  * per-pixel argmax of Q computed on the device, first maximum wins; labels_N receives N int16. */
 dcrf_status dcrf_current_map(dcrf_t* m, dcrf_mat_t* Q, int16_t* labels_N);
+/* DenseCRF::map(n_iterations) (densecrf.cpp:132-137; not wrapped by densecrf.pyx): inference + currentMap in one call;
+ * Q stays on the device, only the int16 label map crosses PCIe. */
+dcrf_status dcrf_map(dcrf_t* m, int n_iterations, int16_t* labels_N);
 
 /* a batch of independent images of one size with shared kernel parameters (BASELINE cfg 4).  For every
  * image b the call does what a caller of the reference does per image --
@@ -222,6 +225,11 @@ dcrf_status dcrf_set_iteration_mode(dcrf_t* m, int mode);
  * so Q equals the reference's to the last bit except for rare last-ulp differences in the L%4 tail labels;
  * 1 = fast softmax in the fused kernel: ex2-based exp, tree sum, reciprocal multiply (~1e-6 relative). */
 dcrf_status dcrf_set_softmax_mode(dcrf_t* m, int fast);
+/* klDivergence's pairwise sums.  0 (default): double accumulation through a fixed reduction tree -- deterministic, and
+ * within ~1e-4 relative of the reference, whose own float reduction (densecrf.cpp:232) is the less accurate side.
+ * 1: the reference's reduction order restated (eight sequential float chains, Eigen's redux): the pairwise terms come
+ * out bit-exact, the whole KL within 1e-9 relative; about 10 ms per term at 1080p instead of 0.1 ms. */
+dcrf_status dcrf_set_kl_mode(dcrf_t* m, int mode);
 /* Which build of the iteration kernels runs (bit mask; every combination gives identical results): 1 = wide-lane
  * update kernel (one 256-bit access per lane, csrc/filter_wide.cu), 2 = the update kernel hands Q * diag(norm_k) to the
  * next iteration's splats.  Default: $DCRF_B200_VARIANT, else 3.  For A/B timing and tests. */

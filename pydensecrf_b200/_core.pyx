@@ -47,6 +47,7 @@ cdef extern from "dcrf_b200.h" nogil:
     int dcrf_step_inference(dcrf_t* m, dcrf_mat_t* Q, dcrf_mat_t* t1, dcrf_mat_t* t2)
     int dcrf_kl_divergence(dcrf_t* m, dcrf_mat_t* Q, double* out)
     int dcrf_current_map(dcrf_t* m, dcrf_mat_t* Q, int16_t* labels)
+    int dcrf_map(dcrf_t* m, int n, int16_t* labels)
     int dcrf_mat_create_empty(dcrf_mat_t** out)
     int dcrf_mat_from_host(const float* rowmajor, int rows, int cols, dcrf_mat_t** out)
     int dcrf_vec_from_host(const float* data, int n, dcrf_mat_t** out)
@@ -77,6 +78,7 @@ cdef extern from "dcrf_b200.h" nogil:
     int dcrf_set_iteration_mode(dcrf_t* m, int mode)
     int dcrf_set_softmax_mode(dcrf_t* m, int fast)
     int dcrf_set_kernel_variant(dcrf_t* m, int mask)
+    int dcrf_set_kl_mode(dcrf_t* m, int mode)
     int dcrf_set_matrix_mode(dcrf_t* m, int mode)
     int dcrf_host_alloc(size_t nbytes, void** out)
     void dcrf_host_free(void* p, size_t nbytes)
@@ -720,6 +722,18 @@ cdef class DenseCRF:
         _check(st)
         return out
 
+    def map(self, int n_iterations):
+        """DenseCRF::map (densecrf.cpp:132-137): inference(n_iterations) followed by currentMap; Q never leaves the GPU.
+        int16 array of length nvar."""
+        import numpy as np
+        out = pinned_empty((self._nvar,), np.int16)
+        cdef int16_t[::1] o = out
+        cdef int st
+        with nogil:
+            st = dcrf_map(self._h, n_iterations, &o[0])
+        _check(st)
+        return out
+
     def synchronize(self):
         cdef int st
         with nogil:  # other Python threads keep driving their own models while this one waits
@@ -771,6 +785,12 @@ cdef class DenseCRF:
     def setSoftmaxMode(self, bint fast):
         """False (default): bit-faithful softmax; True: faster approximate softmax (~1e-6 relative)."""
         _check(dcrf_set_softmax_mode(self._h, 1 if fast else 0))
+
+    def setKLMode(self, int mode):
+        """0 (default): klDivergence sums in double through a fixed tree (deterministic, ~1e-4 relative of the reference,
+        whose float reduction is the less accurate side); 1: the reference's float reduction order restated (pairwise terms
+        bit-exact, slower)."""
+        _check(dcrf_set_kl_mode(self._h, mode))
 
     def _set_kernel_variant(self, int mask):
         """Bit mask: 1 wide-lane update kernel, 2 pre-scaled Q copies for the splats.  Identical results; for A/B timing."""

@@ -235,7 +235,9 @@ struct dcrf_model {
   std::vector<Term*> terms;
   float* acc = nullptr;  // staged path: running tmp1
   float* msg = nullptr;  // staged path / KL: one message
-  double* kl_sums = nullptr;
+  double* kl_sums = nullptr;   // 3 sums + the per-block partials of the ordered reduction
+  dcrf_mat* map_q = nullptr;   // result matrix of dcrf_map (kept: same device buffer -> same CUDA graph on every call)
+  int kl_mode = 0;             // 0: ordered double sums; 1: pairwise terms in the reference's float reduction order
   int iter_mode = 0;
   bool fast_softmax = false;
   int variant = 0;      // kernel variants, see default_variant()
@@ -326,7 +328,7 @@ dcrf_model* model_new(int N, int L, int W, int H, int device) {
   DCRF_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
   DCRF_CUDA(cudaEventCreate(&m->t0));
   DCRF_CUDA(cudaEventCreate(&m->t1));
-  m->kl_sums = dev_alloc<double>(3, m->stream);
+  m->kl_sums = dev_alloc<double>(3 + kl_partials(), m->stream);
   m->use_graphs = std::getenv("DCRF_B200_NO_GRAPHS") == nullptr;
   m->variant = default_variant();
   return m;
@@ -962,6 +964,7 @@ dcrf_status dcrf_create_2d(int width, int height, int nlabels, int device, dcrf_
 }
 void dcrf_destroy(dcrf_t* m) {
   if (!m) return;
+  if (m->map_q) dcrf_mat_destroy(m->map_q);
   try {
     DeviceGuard g(m->device);
     cudaStreamSynchronize(m->stream);
@@ -1262,10 +1265,14 @@ dcrf_status dcrf_kl_divergence(dcrf_t* m, dcrf_mat_t* Q, double* out) {
     float* q = mat_device(m, Q, true);
     ensure_scratch(m);
     DCRF_CUDA(cudaMemsetAsync(m->kl_sums, 0, 3 * sizeof(double), m->stream));
-    launch_kl_terms(cx, m->rl, m->N, q, m->U, nullptr, m->kl_sums);
+    double* part = m->kl_sums + 3;
+    launch_kl_terms(cx, m->rl, m->N, q, m->U, nullptr, m->kl_sums, part);
     for (Term* t : m->terms) {
       term_apply(m, t, q, SLICE_WRITE, false, m->acc);
-      launch_kl_terms(cx, m->rl, m->N, q, nullptr, m->acc, m->kl_sums);
+      if (m->kl_mode == 1)
+        launch_kl_pair_exact(cx, m->rl, m->N, q, m->acc, m->kl_sums + 2);
+      else
+        launch_kl_terms(cx, m->rl, m->N, q, nullptr, m->acc, m->kl_sums, part);
     }
     DCRF_CUDA(cudaEventRecord(Q->ready, m->stream));
     double h[3];
@@ -1286,6 +1293,17 @@ dcrf_status dcrf_current_map(dcrf_t* m, dcrf_mat_t* Q, int16_t* labels_N) {
     dev_free(d, m->stream);
     DCRF_CUDA(cudaStreamSynchronize(m->stream));
   });
+}
+
+dcrf_status dcrf_map(dcrf_t* m, int n_iterations, int16_t* labels_N) {
+  if (!m || !labels_N) {
+    g_last_error = "null argument";
+    return DCRF_EINVAL;
+  }
+  if (!m->map_q) m->map_q = new dcrf_mat();
+  dcrf_status st = dcrf_inference_into(m, n_iterations, m->map_q);
+  if (st == DCRF_OK) st = dcrf_current_map(m, m->map_q, labels_N);
+  return st;
 }
 
 // ---- matrices ------------------------------------------------------------------------------------
@@ -1664,6 +1682,12 @@ dcrf_status dcrf_set_matrix_mode(dcrf_t* m, int mode) {
     DCRF_REQUIRE(m && mode >= 0 && mode <= 2, "bad matrix compatibility mode");
     m->matrix_mode = mode;
     m->drop_graphs();
+  });
+}
+dcrf_status dcrf_set_kl_mode(dcrf_t* m, int mode) {
+  return guarded([&] {
+    DCRF_REQUIRE(m && (mode == 0 || mode == 1), "bad KL mode");
+    m->kl_mode = mode;
   });
 }
 dcrf_status dcrf_set_kernel_variant(dcrf_t* m, int mask) {

@@ -257,8 +257,12 @@ void launch_fill(Ctx cx, float* p, size_t n, float v);
 void launch_norm_transform(Ctx cx, int N, float* norm, bool symmetric);
 // U = Lmat * f for the logistic unary (unary.cpp:50-52); rows_NxLp out
 void launch_logistic_unary(Ctx cx, RowLayout rl, int N, int F, const float* Lmat_LxF, const float* f_FxN, float* U);
-// sums[0] += sum Q log max(Q,1e-20), sums[1] += sum U*Q, sums[2] += sum Q*T   (double accumulators on the device)
-void launch_kl_terms(Ctx cx, RowLayout rl, int N, const float* Q, const float* U, const float* T, double* sums);
+// sums[0] += sum Q log max(Q,1e-20), sums[1] += sum U*Q (T == null) or sums[2] += sum Q*T: double accumulators on the
+// device, fixed reduction tree through `part` (kl_partials() doubles): deterministic
+void launch_kl_terms(Ctx cx, RowLayout rl, int N, const float* Q, const float* U, const float* T, double* sums, double* part);
+size_t kl_partials();
+// *sum += (Q.array() * T.array()).sum() as the reference's float Eigen reduction evaluates it (bit-exact, sequential)
+void launch_kl_pair_exact(Ctx cx, RowLayout rl, int N, const float* Q, const float* T, double* sum);
 void launch_argmax(Ctx cx, RowLayout rl, int N, const float* Q, int16_t* labels);
 void launch_argmax64(Ctx cx, RowLayout rl, int N, const float* Q, long long* labels);
 

@@ -177,6 +177,49 @@ def mid():
          ref_margin=(srt[-1] - srt[-2]).astype(np.float32), ref_Q_sub=Q[:, ::5].copy())
 
 
+def _utils_cases():
+    """Inputs for the utils goldens: (name, function name, args, kwargs)."""
+    rng = np.random.default_rng(21)
+    lab2 = rng.integers(0, 5, (6, 7))
+    sm3 = rng.random((4, 5, 6)).astype(np.float32)
+    sm3 /= sm3.sum(0, keepdims=True)
+    sm64 = rng.random((3, 11))
+    sm64 /= sm64.sum(0, keepdims=True)
+    im_hwc = rng.integers(0, 256, (5, 7, 3), dtype=np.uint8)
+    im_chw = np.ascontiguousarray(np.moveaxis(im_hwc, 2, 0))
+    vol = rng.integers(0, 256, (3, 4, 5), dtype=np.uint8)
+    fim = rng.random((4, 6, 2)).astype(np.float32)
+    return [
+        ("labels_unsure", "unary_from_labels", (lab2, 4, 0.7), {"zero_unsure": True}),
+        ("labels_sure", "unary_from_labels", (lab2, 5, 0.55), {"zero_unsure": False}),
+        ("compute_unary", "compute_unary", (lab2, 4), {"GT_PROB": 0.8}),
+        ("softmax_default", "unary_from_softmax", (sm3,), {}),
+        ("softmax_scale", "unary_from_softmax", (sm3,), {"scale": 0.7, "clip": 1e-3}),
+        ("softmax_noclip", "unary_from_softmax", (sm3 + 1e-3,), {"scale": 1.0, "clip": None}),
+        ("softmax_f64", "unary_from_softmax", (sm64,), {"scale": 0.25}),
+        ("softmax_to_unary", "softmax_to_unary", (sm3 + 1e-4,), {"GT_PROB": 0.9}),
+        ("gauss_2d", "create_pairwise_gaussian", ((3, 2.5), (5, 7)), {}),
+        ("gauss_3d", "create_pairwise_gaussian", ((1, 2, 3), (3, 4, 5)), {}),
+        ("bilat_chdim2", "create_pairwise_bilateral", ((80, 60), (13, 11, 9), im_hwc), {"chdim": 2}),
+        ("bilat_chdim0", "create_pairwise_bilateral", ((3, 3), 13, im_chw), {"chdim": 0}),
+        ("bilat_nochan", "create_pairwise_bilateral", ((3, 3, 3), (13,), vol), {"chdim": -1}),
+        ("bilat_float", "create_pairwise_bilateral", ((2, 2), (0.1, 0.2), fim), {"chdim": 2}),
+    ]
+
+
+def utils_golden():
+    """Outputs of the reference's own pydensecrf/utils.py (pure numpy, imported by path) on fixed inputs."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("ref_utils", "/root/reference/pydensecrf/utils.py")
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    out = {}
+    for name, fn, args, kw in _utils_cases():
+        out["ref_" + name] = getattr(ref, fn)(*args, **kw)
+    save("utils.npz", **out)
+
+
 if __name__ == "__main__":
     po.build()
     assert po.available("ref"), "oracle/_ref/libref.so missing: /root/reference not visible?"
@@ -186,3 +229,4 @@ if __name__ == "__main__":
     model_small()
     cfg1()
     mid()
+    utils_golden()

@@ -1,0 +1,137 @@
+"""Round-2 additions on the GPU: kernel variants (identical bits), klDivergence modes, DenseCRF.map, live host views."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dcrf():
+    import pydensecrf_b200.densecrf as m
+
+    assert m.device_count() >= 1
+    return m
+
+
+def _model(dcrf, W, H, L, seed, nt=None, compat=(3.0, 10.0)):
+    from tests import workloads as wl
+
+    img = wl.smooth_image(H, W, seed=seed, grid=8)
+    U = wl.softmax_unary(H, W, L, seed=seed, grid=8)
+    d = dcrf.DenseCRF2D(W, H, L)
+    d.setUnaryEnergy(U)
+    kw = {} if nt is None else {"normalization": dcrf.NormalizationType(nt)}
+    d.addPairwiseGaussian(3, compat[0], **kw)
+    d.addPairwiseBilateral(40, 13, img, compat[1], **kw)
+    return d, U, img
+
+
+@pytest.mark.parametrize("L", [3, 8, 21, 24])
+@pytest.mark.parametrize("nt", [0, 1, 2, 3])
+def test_kernel_variants_give_identical_bits(dcrf, L, nt):
+    """mask 1: wide-lane update kernel (LDG.256, only instantiated for 21 labels); mask 2: the update kernel hands the
+    pre-scaled Q to the next splat.  Same float operations in the same order: inference, graph replay and stepInference
+    agree bit for bit across all four combinations, for every normalisation type."""
+    d, U, img = _model(dcrf, 61, 45, L, seed=L + nt, nt=nt)
+    ref = None
+    for mask in (0, 1, 2, 3):
+        d._set_kernel_variant(mask)
+        q = [np.array(d.inference(n)) for n in (0, 1, 4)]
+        q += [np.array(d.inference(4)) for _ in range(3)]   # third identical call replays the captured graph
+        Qs, t1, t2 = d.startInference()
+        for _ in range(2):
+            d.stepInference(Qs, t1, t2)
+        q.append(np.array(Qs))
+        if ref is None:
+            ref = q
+        for a, b in zip(q, ref):
+            assert np.array_equal(a, b), (L, nt, mask)
+    assert np.array_equal(ref[2], ref[3]) and np.array_equal(ref[2], ref[5])
+
+
+def test_variants_match_the_oracle(dcrf, oracle_built):
+    d, U, img = _model(dcrf, 70, 50, 21, seed=11)
+    o = oracle_built.CRF((70, 50), 21, "orc")
+    o.setUnaryEnergy(U)
+    o.addPairwiseGaussian(3, 3.0)
+    o.addPairwiseBilateral(40, 13, img, 10.0)
+    Qo = o.inference(6)
+    for mask in (0, 3):
+        d._set_kernel_variant(mask)
+        assert np.abs(np.array(d.inference(6)) - Qo).max() <= 2e-6
+
+
+def test_kl_modes(dcrf, oracle_built):
+    """Default: ordered double sums (deterministic; the reference's float reduction of each pairwise term is the less
+    accurate side: relative 1e-4).  Mode 1 restates that float reduction: pairwise terms bit-exact, total within 1e-9."""
+    for (W, H, L) in ((64, 48, 21), (33, 20, 2), (19, 11, 5)):
+        d, U, img = _model(dcrf, W, H, L, seed=W)
+        o = oracle_built.CRF((W, H), L, "orc")
+        o.setUnaryEnergy(U)
+        o.addPairwiseGaussian(3, 3.0)
+        o.addPairwiseBilateral(40, 13, img, 10.0)
+        Qd = d.inference(3)
+        Qo = np.array(Qd)   # the same Q on both sides: isolates the KL arithmetic
+        klo = o.klDivergence(Qo)
+        d.setKLMode(0)
+        kls = [d.klDivergence(Qd) for _ in range(4)]
+        assert len(set(kls)) == 1                      # run-to-run deterministic
+        assert abs(kls[0] - klo) <= 1e-4 * abs(klo)
+        d.setKLMode(1)
+        kle = d.klDivergence(Qd)
+        assert abs(kle - klo) <= 1e-9 * abs(klo), (kle, klo)
+
+
+def test_map_equals_inference_plus_argmax(dcrf):
+    d, U, img = _model(dcrf, 47, 31, 21, seed=2)
+    lab = d.map(5)
+    Q = d.inference(5)
+    assert lab.dtype == np.int16 and lab.shape == (47 * 31,)
+    assert np.array_equal(lab, np.argmax(np.array(Q), axis=0))
+    assert np.array_equal(lab, d.currentMap(Q))
+    assert np.array_equal(d.map(5), lab)
+
+
+def test_writes_through_a_live_view_are_honoured(dcrf, oracle_built):
+    """The reference's matrices share memory with their numpy views (eigen.pyx:40,92): an edit made through a view that is
+    still alive must be what the next stepInference / klDivergence / currentMap / np.argmax sees."""
+    d, U, img = _model(dcrf, 40, 30, 21, seed=5)
+    Q, t1, t2 = d.startInference()
+    v = np.asarray(Q)                     # live, writable view
+    rng = np.random.default_rng(0)
+    init = rng.random(v.shape).astype(np.float32)
+    init /= init.sum(0, keepdims=True)
+    v[...] = init                         # no step in between
+    assert np.array_equal(np.argmax(Q, axis=0), np.argmax(init, axis=0))       # dispatch must not answer from a stale device copy
+    assert np.array_equal(d.currentMap(Q), np.argmax(init, axis=0))
+    o = oracle_built.CRF((40, 30), 21, "orc")
+    o.setUnaryEnergy(U)
+    o.addPairwiseGaussian(3, 3.0)
+    o.addPairwiseBilateral(40, 13, img, 10.0)
+    Qo = init.copy()
+    assert abs(d.klDivergence(Q) - o.klDivergence(Qo)) <= 1e-4 * abs(o.klDivergence(Qo))
+    d.stepInference(Q, t1, t2)
+    o.stepInference(Qo)
+    assert np.abs(v - Qo).max() <= 2e-6   # and the live view observes the update
+
+
+def test_matrix_passed_between_models_is_ordered(dcrf):
+    """A Q produced on one model's stream and consumed by another model (own stream, same GPU) right away."""
+    d1, U, img = _model(dcrf, 96, 64, 21, seed=8)
+    d2, _, _ = _model(dcrf, 96, 64, 21, seed=8)
+    want = None
+    for _ in range(5):
+        Q = d1.inference(3)
+        lab = d2.currentMap(Q)            # reads Q on d2's stream: must wait for d1's kernels
+        kl = d2.klDivergence(Q)
+        if want is None:
+            want = (lab.copy(), kl)
+        assert np.array_equal(lab, want[0]) and kl == want[1]
+
+
+def test_cuda_array_interface_probe_on_host_matrix():
+    import pydensecrf_b200.eigen as e
+
+    m = e.matrixXf(np.ones((3, 4), np.float32))
+    assert not hasattr(m, "__cuda_array_interface__")   # AttributeError, not ValueError: hasattr-style probes work
+    assert np.array(m).shape == (3, 4)
