@@ -124,16 +124,20 @@ dcrf_status dcrf_current_map(dcrf_t* m, dcrf_mat_t* Q, int16_t* labels_N);
  * Q stays on the device, only the int16 label map crosses PCIe. */
 dcrf_status dcrf_map(dcrf_t* m, int n_iterations, int16_t* labels_N);
 
-/* a batch of independent images of one size with shared kernel parameters (BASELINE cfg 4).  For every
- * image b the call does what a caller of the reference does per image --
+/* a batch of independent images of one size with shared kernel parameters (BASELINE cfg 4).  For
+ * every image b the call does what a caller of the reference does per image --
  *   d = DenseCRF2D(W, H, L); d.setUnaryEnergy(unary[b]); d.addPairwiseGaussian((g_sx, g_sy), g_w);
  *   d.addPairwiseBilateral((b_sx, b_sy), (b_sr, b_sg, b_sb), rgb[b], b_w); Q = d.inference(n_iterations); MAP = argmax(Q)
- * (examples/inference.py:69-122; Potts compatibilities, NORMALIZE_SYMMETRIC) -- from n_workers host threads (0 = 4), each
- * with its own model and stream, so that lattice construction, uploads and kernels of different images overlap on the
- * device.  Results are identical to the per-image calls.  labels[b] receives N int16; q_out (may be NULL) points to B
- * arrays of L*N floats that receive Q in the (L, N) row-major layout of np.array(Q).
+ * (examples/inference.py:69-122; Potts compatibilities, NORMALIZE_SYMMETRIC) -- with identical results, but chunks of
+ * about 4 MPix of images are run as ONE model ("super-lattice"): the images are stacked, both lattices are built once per
+ * chunk with the image index as an extra key coordinate, and every kernel runs once over the chunk.  n_workers host
+ * threads (0 = 3 per GPU) each drive their own chunk: one chunk at a time owns a GPU's SMs, the uploads and the
+ * host-side delivery of the others run beside it.
+ * ($DCRF_B200_BATCH_MODE=0, or W*H not a multiple of 4: one model per image from 4 workers per GPU, as in round 1.)
+ * labels[b] receives N int16; q_out (may be NULL) points to B arrays of L*N floats that receive Q in the (L, N) row-major
+ * layout of np.array(Q).
  * Several GPUs (replicas, no collective): devices[0..n_devices) lists them and worker k drives devices[k %
- * n_devices] (n_workers then defaults to 4 per device); with devices == NULL everything runs on `device` (-1 = default). */
+ * n_devices]; with devices == NULL everything runs on `device` (-1 = default). */
 dcrf_status dcrf_batch_map_2d(int W, int H, int L, int device, int B, const float* const* unary_LxN,
                               const uint8_t* const* rgb_HxWx3, float g_sx, float g_sy, float g_w, float b_sx, float b_sy,
                               float b_sr, float b_sg, float b_sb, float b_w, int n_iterations, int n_workers,

@@ -228,6 +228,7 @@ struct Term {
 
 struct dcrf_model {
   int N = 0, L = 0, W = 0, H = 0, device = 0;
+  int npi = 0;  // > 0: the variables are N / npi images of npi pixels stacked along y (internal batch models)
   RowLayout rl;
   cudaStream_t stream = nullptr;
   Profiler prof;
@@ -748,8 +749,7 @@ class CopyPool {
 };
 static CopyPool& g_copy_pool = *new CopyPool();  // never destroyed: its detached helpers may outlive static destructors
 
-float* upload_tmp(dcrf_model* m, const void* host, size_t bytes) {
-  char* d = dev_alloc<char>(bytes, m->stream);
+void upload_to(dcrf_model* m, char* d, const void* host, size_t bytes) {
   static const int nthreads = [] {
     const char* e = std::getenv("DCRF_B200_UPLOAD_THREADS");
     return e ? std::max(0, std::atoi(e)) : 4;
@@ -759,7 +759,7 @@ float* upload_tmp(dcrf_model* m, const void* host, size_t bytes) {
   cudaGetLastError();
   if (!pageable || nthreads == 0 || bytes < (4u << 20)) {
     DCRF_CUDA(cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, m->stream));
-    return (float*)d;
+    return;
   }
   const size_t mb = 1u << 20;
   const size_t chunk = std::min((size_t)32 * mb, std::max((size_t)2 * mb, ((bytes / 4 + mb - 1) / mb) * mb));
@@ -782,12 +782,20 @@ float* upload_tmp(dcrf_model* m, const void* host, size_t bytes) {
       if (done[k]) cudaEventDestroy(done[k]);
       g_pinned.put(stage[k], chunk);
     }
-    dev_free(d, m->stream);
     throw;
   }
   for (int k = 0; k < 2; k++) {
     cudaEventDestroy(done[k]);
     g_pinned.put(stage[k], chunk);
+  }
+}
+float* upload_tmp(dcrf_model* m, const void* host, size_t bytes) {
+  char* d = dev_alloc<char>(bytes, m->stream);
+  try {
+    upload_to(m, d, host, bytes);
+  } catch (...) {
+    dev_free(d, m->stream);
+    throw;
   }
   return (float*)d;
 }
@@ -814,9 +822,11 @@ float* raw_norm(dcrf_model* m, const Lattice& lat) {
 }
 
 struct GeoKey {
-  int device, W, H;
+  int device, W, H, npi;
   uint32_t sx, sy;
-  bool operator==(const GeoKey& o) const { return device == o.device && W == o.W && H == o.H && sx == o.sx && sy == o.sy; }
+  bool operator==(const GeoKey& o) const {
+    return device == o.device && W == o.W && H == o.H && npi == o.npi && sx == o.sx && sy == o.sy;
+  }
 };
 // most recent last, at most 4 entries; heap objects that are never destroyed, so that no CUDA call runs from a static
 // destructor at process exit (entries still referenced by live models stay alive through their shared_ptr anyway)
@@ -829,7 +839,7 @@ std::shared_ptr<SharedLattice> shared_gaussian_lattice(dcrf_model* m, const Feat
     const char* e = std::getenv("DCRF_B200_NO_LATTICE_CACHE");
     return e && std::atoi(e) != 0;
   }();
-  GeoKey key{m->device, m->W, m->H, 0, 0};
+  GeoKey key{m->device, m->W, m->H, m->npi, 0, 0};
   std::memcpy(&key.sx, &src.s[0], 4);
   std::memcpy(&key.sy, &src.s[1], 4);
   if (!off) {
@@ -839,7 +849,7 @@ std::shared_ptr<SharedLattice> shared_gaussian_lattice(dcrf_model* m, const Feat
   }
   auto sp = std::make_shared<SharedLattice>();
   sp->device = m->device;
-  lattice_build(m->cx(), src, 2, m->N, &sp->lat);
+  lattice_build(m->cx(), src, 2, m->N, &sp->lat, m->npi);
   sp->norm_raw = raw_norm(m, sp->lat);
   DCRF_CUDA(cudaGetLastError());
   DCRF_CUDA(cudaStreamSynchronize(m->stream));  // complete before any other stream may read it
@@ -866,7 +876,7 @@ void add_term(dcrf_model* m, const FeatureSource& src, int d, int compat_kind, c
       t->shared = shared_gaussian_lattice(m, src);
       t->lat = t->shared->lat;  // pointers only; owned by the shared object
     } else {
-      lattice_build(cx, src, d, m->N, &t->lat);
+      lattice_build(cx, src, d, m->N, &t->lat, m->npi);
     }
     t->ntype = ntype;
     t->ckind = compat_kind;
@@ -907,10 +917,13 @@ void add_term(dcrf_model* m, const FeatureSource& src, int d, int compat_kind, c
       std::vector<float> h(N);
       DCRF_CUDA(cudaMemcpyAsync(h.data(), t->norm, (size_t)N * sizeof(float), cudaMemcpyDeviceToHost, s));
       DCRF_CUDA(cudaStreamSynchronize(s));
-      float mean = 0.f;
-      for (int i = 0; i < N; i++) mean += h[i];
-      mean = (float)N / mean;
-      launch_fill(cx, t->norm, N, mean);
+      const int per = m->npi > 0 ? m->npi : N;  // a batch: every image has its own mean, as separate models would
+      for (int i0 = 0; i0 < N; i0 += per) {
+        float mean = 0.f;
+        for (int i = i0; i < i0 + per; i++) mean += h[i];
+        mean = (float)per / mean;
+        launch_fill(cx, t->norm + i0, per, mean);
+      }
     } else {
       launch_norm_transform(cx, N, t->norm, ntype == DCRF_NORMALIZE_SYMMETRIC);
     }
@@ -1082,6 +1095,7 @@ dcrf_status dcrf_add_pairwise_gaussian(dcrf_t* m, float sx, float sy, int compat
     FeatureSource src{};
     src.kind = FEAT_GAUSS2D;
     src.W = m->W;
+    src.H = m->npi > 0 ? m->npi / m->W : 0;
     src.s[0] = sx, src.s[1] = sy;
     add_term(m, src, 2, compat_kind, compat_data, kernel_type, norm_type);
   });
@@ -1097,6 +1111,7 @@ dcrf_status dcrf_add_pairwise_bilateral(dcrf_t* m, float sx, float sy, float sr,
     FeatureSource src{};
     src.kind = FEAT_BILATERAL2D;
     src.W = m->W;
+    src.H = m->npi > 0 ? m->npi / m->W : 0;
     src.rgb = im;
     src.s[0] = sx, src.s[1] = sy, src.s[2] = sr, src.s[3] = sg, src.s[4] = sb;
     try {
@@ -1500,6 +1515,146 @@ dcrf_status dcrf_flush_l2(dcrf_t* m) {
   });
 }
 
+}  // extern "C"
+
+namespace {
+
+struct BatchParams {
+  int W, H, L, n_iterations;
+  float g_sx, g_sy, g_w, b_sx, b_sy, b_sr, b_sg, b_sb, b_w;
+};
+
+// Images [b0, b0 + Bc) as ONE model of Bc * W * H variables ("super-lattice"): the images are stacked along y,
+// both lattices are built once for the whole chunk with the image index as an extra key coordinate (lattice.cu), and
+// every kernel of the iteration runs once over the chunk -- at the efficiency of a large image instead of Bc small
+// ones.  Tables, ids and arithmetic per image are exactly those of a separate model, so the results are bit-identical.
+// Two phases so that a worker can upload its next chunk while another worker's chunk owns the SMs: upload() moves the
+// unaries and images (copy engine + one transposition launch), compute() does everything else under the device's lock.
+struct BatchChunk {
+  const BatchParams& p;
+  int b0, Bc;
+  size_t Ni, N;
+  dcrf_model* m = nullptr;
+  uint8_t* im = nullptr;
+  BatchChunk(const BatchParams& p_, int dev, int b0_, int Bc_) : p(p_), b0(b0_), Bc(Bc_) {
+    Ni = (size_t)p.W * p.H, N = Ni * Bc;
+    m = model_new((int)N, p.L, p.W, p.H * Bc, dev);
+    m->npi = (int)Ni;
+    m->use_graphs = false;  // one inference per model
+  }
+  ~BatchChunk() {
+    if (m) {
+      dev_free(im, m->stream);
+      dcrf_destroy(m);
+    }
+  }
+  void upload(const float* const* unary, const uint8_t* const* rgb) {
+    DeviceGuard g(m->device);
+    cudaStream_t s = m->stream;
+    const int L = p.L;
+    // unaries: every image's (L, Ni) planes into one staging buffer, one transposition launch for the chunk
+    float* planes = dev_alloc<float>(N * L, s);
+    for (int b = 0; b < Bc; b++) upload_to(m, (char*)(planes + (size_t)b * L * Ni), unary[b0 + b], Ni * L * sizeof(float));
+    m->U = dev_alloc<float>(N * m->rl.Lp, s);
+    launch_planes_to_rows(m->cx(), m->rl, (int)Ni, planes, m->U, Bc);
+    dev_free(planes, s);
+    im = dev_alloc<uint8_t>(N * 3, s);
+    for (int b = 0; b < Bc; b++) upload_to(m, (char*)(im + (size_t)b * Ni * 3), rgb[b0 + b], Ni * 3);
+    DCRF_CUDA(cudaGetLastError());
+    DCRF_CUDA(cudaStreamSynchronize(s));  // the caller's buffers are free again; compute() starts from resident data
+  }
+  void compute(int16_t* const* labels, float* const* q_out) {
+    DeviceGuard g(m->device);
+    cudaStream_t s = m->stream;
+    Ctx cx = m->cx();
+    const int L = p.L, Lp = m->rl.Lp;
+    FeatureSource src{};
+    src.kind = FEAT_GAUSS2D;
+    src.W = p.W, src.H = p.H;
+    src.s[0] = p.g_sx, src.s[1] = p.g_sy;
+    add_term(m, src, 2, DCRF_COMPAT_POTTS, &p.g_w, 1, DCRF_NORMALIZE_SYMMETRIC);
+    src.kind = FEAT_BILATERAL2D;
+    src.rgb = im;
+    src.s[0] = p.b_sx, src.s[1] = p.b_sy, src.s[2] = p.b_sr, src.s[3] = p.b_sg, src.s[4] = p.b_sb;
+    add_term(m, src, 5, DCRF_COMPAT_POTTS, &p.b_w, 1, DCRF_NORMALIZE_SYMMETRIC);
+    dev_free(im, s);
+    im = nullptr;
+    float* q = dev_alloc<float>(N * Lp, s);
+    for (Term* t : m->terms) ensure_val(m, t);
+    ensure_scratch_if_staged(m);
+    if (p.n_iterations > 0 && prescale_wanted(m)) ensure_qn(m);
+    ensure_aux(m, (int)m->terms.size());
+    mf_run(m, q, p.n_iterations);
+    int16_t* dl = dev_alloc<int16_t>(N, s);
+    launch_argmax(cx, m->rl, (int)N, q, dl);
+    int16_t* hl = (int16_t*)g_pinned.get(N * sizeof(int16_t));
+    float* hq = nullptr;
+    try {
+      DCRF_CUDA(cudaMemcpyAsync(hl, dl, N * sizeof(int16_t), cudaMemcpyDeviceToHost, s));
+      if (q_out) {
+        float* packed = dev_alloc<float>(N * L, s);
+        launch_pack_rows(cx, m->rl, (int)N, q, packed);
+        hq = (float*)g_pinned.get(N * L * sizeof(float));
+        DCRF_CUDA(cudaMemcpyAsync(hq, packed, N * L * sizeof(float), cudaMemcpyDeviceToHost, s));
+        dev_free(packed, s);
+      }
+      dev_free(dl, s);
+      dev_free(q, s);
+      DCRF_CUDA(cudaGetLastError());
+      DCRF_CUDA(cudaStreamSynchronize(s));
+    } catch (...) {
+      cudaStreamSynchronize(s);
+      g_pinned.put(hl, N * sizeof(int16_t));
+      if (hq) g_pinned.put(hq, N * L * sizeof(float));
+      throw;
+    }
+    hl_ = hl, hq_ = hq;
+    (void)labels;
+    (void)q_out;
+  }
+  // host-side scatter of the results into the caller's per-image arrays (outside the device lock)
+  void deliver(int16_t* const* labels, float* const* q_out) {
+    const int L = p.L;
+    for (int b = 0; b < Bc; b++) {
+      std::memcpy(labels[b0 + b], hl_ + (size_t)b * Ni, Ni * sizeof(int16_t));
+      if (hq_ && q_out && q_out[b0 + b]) {  // Eigen layout (Ni columns of L floats) -> (L, Ni) row-major for the caller
+        const float* src_q = hq_ + (size_t)b * Ni * L;
+        float* dst = q_out[b0 + b];
+        for (size_t i = 0; i < Ni; i++)
+          for (int l = 0; l < L; l++) dst[(size_t)l * Ni + i] = src_q[i * L + l];
+      }
+    }
+    g_pinned.put(hl_, N * sizeof(int16_t));
+    if (hq_) g_pinned.put(hq_, N * L * sizeof(float));
+    hl_ = nullptr, hq_ = nullptr;
+  }
+  int16_t* hl_ = nullptr;
+  float* hq_ = nullptr;
+};
+
+// one chunk at a time owns a device's SMs (the kernels of two chunks would only evict each other's L2 lines); uploads
+// and the host-side delivery of other chunks run beside it
+std::mutex& device_lock(int dev) {
+  static std::mutex* locks = new std::mutex[64];
+  return locks[((dev < 0 ? 0 : dev)) & 63];
+}
+
+// images per chunk of the super-lattice path: large enough for full-size kernels, small enough that the upload of one
+// chunk hides under the kernels of another (about 0.25 GB of device memory per 512x512 image and chunk in flight)
+int batch_chunk_images(int W, int H, int L) {
+  const char* e = std::getenv("DCRF_B200_BATCH_CHUNK");  // read per call: tests vary it
+  const int env = e ? std::atoi(e) : 0;
+  const int64_t Ni = (int64_t)W * H, Lp = RowLayout(L).Lp;
+  int64_t c = env > 0 ? env : std::max<int64_t>(1, (4ll << 20) / Ni);  // ~4 MPix per chunk
+  c = std::min<int64_t>(c, ((1ll << 31) - 64) / (Ni * 6));              // contribution indices stay below 2^31 (d = 5)
+  c = std::min<int64_t>(c, ((1ll << 31) - 64) / (Ni * Lp));             // 32-bit row offsets of the fused kernel
+  return (int)std::max<int64_t>(c, 1);
+}
+
+}  // namespace
+
+extern "C" {
+
 dcrf_status dcrf_batch_map_2d(int W, int H, int L, int device, int B, const float* const* unary_LxN,
                               const uint8_t* const* rgb_HxWx3, float g_sx, float g_sy, float g_w, float b_sx, float b_sy,
                               float b_sr, float b_sg, float b_sb, float b_w, int n_iterations, int n_workers,
@@ -1509,20 +1664,51 @@ dcrf_status dcrf_batch_map_2d(int W, int H, int L, int device, int B, const floa
     DCRF_REQUIRE(B == 0 || (unary_LxN && rgb_HxWx3 && labels), "null argument");
     DCRF_REQUIRE(n_devices >= 0 && (n_devices == 0 || devices), "bad device list");
     const int ndev = devices ? std::max(n_devices, 1) : 1;
-    const int nw = std::max(1, std::min(n_workers > 0 ? n_workers : 4 * ndev, B));
+    // $DCRF_B200_BATCH_MODE: 1 (default) = chunks of images as one super-lattice model; 0 = one model per image
+    const char* mode_env = std::getenv("DCRF_B200_BATCH_MODE");
+    const int mode = mode_env ? std::atoi(mode_env) : 1;
+    const int chunk = batch_chunk_images(W, H, L);
+    const bool super = mode != 0 && ((int64_t)W * H) % 4 == 0 && chunk >= 2 && B >= 2;
+    const int nchunks = super ? (B + chunk - 1) / chunk : B;
+    const int nw = std::max(1, std::min(n_workers > 0 ? n_workers : (super ? 3 : 4) * ndev, nchunks));
     std::atomic<int> next_worker{0};
     std::atomic<int> next{0};
     std::atomic<bool> failed{false};
     std::mutex mu;
     std::string first_error;
     dcrf_status first_status = DCRF_OK;
+    const BatchParams bp{W, H, L, n_iterations, g_sx, g_sy, g_w, b_sx, b_sy, b_sr, b_sg, b_sb, b_w};
+    auto fail = [&](dcrf_status st, const std::string& what) {
+      std::lock_guard<std::mutex> g(mu);
+      if (!failed.exchange(true)) {
+        first_status = st;
+        first_error = what;
+      }
+    };
     auto worker = [&] {
       const size_t N = (size_t)W * H;
       const int wk = next_worker.fetch_add(1);
       const int dev = (devices && n_devices > 0) ? devices[wk % n_devices] : device;
       for (;;) {
         const int b = next.fetch_add(1);
-        if (b >= B || failed.load()) return;
+        if (b >= nchunks || failed.load()) return;
+        if (super) {
+          const int b0 = b * chunk, Bc = std::min(chunk, B - b0);
+          try {
+            BatchChunk ch(bp, dev, b0, Bc);
+            ch.upload(unary_LxN, rgb_HxWx3);
+            {
+              std::lock_guard<std::mutex> own(device_lock(ch.m->device));
+              ch.compute(labels, q_out);
+            }
+            ch.deliver(labels, q_out);
+          } catch (const Error& e) {
+            fail(e.code, "images " + std::to_string(b0) + ".." + std::to_string(b0 + Bc - 1) + ": " + e.what());
+          } catch (const std::exception& e) {
+            fail(DCRF_ECUDA, "images " + std::to_string(b0) + ".." + std::to_string(b0 + Bc - 1) + ": " + e.what());
+          }
+          continue;
+        }
         dcrf_t* m = nullptr;
         dcrf_mat_t* Q = nullptr;
         dcrf_status st = dcrf_create_2d(W, H, L, dev, &m);
@@ -1543,13 +1729,7 @@ dcrf_status dcrf_batch_map_2d(int W, int H, int L, int device, int B, const floa
             dcrf_mat_release_host(Q);
           }
         }
-        if (st != DCRF_OK) {
-          std::lock_guard<std::mutex> g(mu);
-          if (!failed.exchange(true)) {
-            first_status = st;
-            first_error = "image " + std::to_string(b) + ": " + dcrf_last_error();
-          }
-        }
+        if (st != DCRF_OK) fail(st, "image " + std::to_string(b) + ": " + dcrf_last_error());
         if (Q) dcrf_mat_destroy(Q);
         if (m) dcrf_destroy(m);
       }

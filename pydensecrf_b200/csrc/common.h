@@ -129,6 +129,7 @@ struct FeatureSource {
   const float* feat;  // device, d x N row-major (FEAT_GENERIC)
   const uint8_t* rgb; // device, N x 3 (FEAT_BILATERAL2D)
   int W;
+  int H;              // image height when the variables are a batch of images stacked along y (0: one image)
   float s[5];         // sx, sy, sr, sg, sb
   // FEAT_ND: what utils.create_pairwise_gaussian / create_pairwise_bilateral build on the host (utils.py:89-162):
   // nsp spatial coordinates (C order over dims[]) / sdims, then nch channels of a channel-last image / schan
@@ -149,13 +150,16 @@ struct Lattice {
   int2* nbr = nullptr;         // [(d+1)*V] rows (id+1) of the -/+ neighbours, 0 = absent
   int* order = nullptr;        // [V] splat work order: windows of 4096 vertex ids, inside a window by CSR row length
   int16_t* keys = nullptr;     // [V*d]
+  int* vimg = nullptr;         // [V] image index of every vertex (batched lattices only)
   float alpha = 1.f;           // 1/(1+2^-d)
   int max_row = 0;             // longest CSR row (diagnostic)
   void release(cudaStream_t s);
 };
 
 static const int kMaxFeatureDims = 32;
-void lattice_build(Ctx cx, const FeatureSource& src, int d, int N, Lattice* out);
+// npi > 0: the N variables are N / npi images of npi pixels; the lattices of the images are built side by side (the image
+// index is an extra key coordinate) and come out concatenated with id offsets, identical to separate builds
+void lattice_build(Ctx cx, const FeatureSource& src, int d, int N, Lattice* out, int npi = 0);
 
 // ---------------------------------------------------------------------------------------------
 // filter / update kernels (filter.cu)
@@ -246,7 +250,8 @@ void launch_matrix_compat_tc(Ctx cx, RowLayout rl, int N, const float* Bhi, cons
                              const float* U, bool neg_unary, float* out);
 
 // layout conversion at the boundary
-void launch_planes_to_rows(Ctx cx, RowLayout rl, int N, const float* planes_LxN, float* rows_NxLp);
+// batch > 1: `batch` images, each with its own (L, N) planes and N consecutive rows
+void launch_planes_to_rows(Ctx cx, RowLayout rl, int N, const float* planes_LxN, float* rows_NxLp, int batch = 1);
 // same transposition with utils.unary_from_softmax (utils.py:55-79) applied on the way: -log(clip(scale*p + (1-scale)/L))
 void launch_softmax_planes_to_unary(Ctx cx, RowLayout rl, int N, const float* planes_LxN, double scale, double clip,
                                     float* rows_NxLp);

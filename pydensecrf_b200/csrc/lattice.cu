@@ -20,6 +20,11 @@
 //                 order instead of as float atomics.
 //   k_neighbours  2(d+1) lookups per vertex.
 //
+// Batches (SURVEY 8e "super-lattice"): with npi > 0 the N variables are B images of npi pixels each and the image
+// index is one more (exact) key coordinate: vertices of different images never meet, the first-touch numbering walks
+// image after image, so tables and ids are the per-image lattices concatenated with id offsets -- bit for bit what B
+// separate builds give -- while every kernel here and in the filter runs once over the whole batch.
+//
 // CUB (bundled with the CUDA toolkit) provides the prefix sums and the radix sort; everything
 // lattice-specific is written here.
 #include <cub/device/device_radix_sort.cuh>
@@ -39,6 +44,7 @@ constexpr int kThreads = 256;
 
 struct ElevateParams {
   int N, Npad, d;
+  int npi;  // pixels per image of a batch (0: one image)
   FeatureSource src;
   float scale[kMaxFeatureDims];
   float inv_dp1, dp1;
@@ -55,7 +61,7 @@ __device__ __forceinline__ float feature_of(const FeatureSource& s, int k, int i
   // DenseCRF2D::addPairwiseGaussian / Bilateral (densecrf.cpp:61-81): int coordinate / byte divided
   // by the float sigma, pixel index = y*W + x
   if (k == 0) return __fdiv_rn((float)(i % s.W), s.s[0]);
-  if (k == 1) return __fdiv_rn((float)(i / s.W), s.s[1]);
+  if (k == 1) return __fdiv_rn((float)(s.H > 0 ? (i / s.W) % s.H : i / s.W), s.s[1]);  // s.H: image height of a batch
   return __fdiv_rn((float)__ldg(s.rgb + (size_t)i * 3 + (k - 2)), s.s[k]);
 }
 
@@ -181,13 +187,16 @@ __device__ __forceinline__ uint64_t hash_key(const int16_t (&k)[MD], int d) {
   return mix64(h);
 }
 
-// does the contribution `cur` (some pixel corner) name the same vertex as key[]?
+__device__ __forceinline__ uint64_t hash_img(uint64_t h, int img) { return mix64(h ^ ((uint64_t)(uint32_t)img * 0x9E3779B97F4A7C15ull)); }
+
+// does the contribution `cur` (some pixel corner) name the same vertex as key[] (of image `img` when npi > 0)?
 template <int MD>
 __device__ __forceinline__ bool same_vertex(uint32_t cur, const int16_t (&key)[MD], int d,
-                                            const int16_t* __restrict__ rem, const uint8_t* __restrict__ rnk) {
+                                            const int16_t* __restrict__ rem, const uint8_t* __restrict__ rnk, int npi, int img) {
   const uint32_t dp1 = d + 1;
   const uint32_t pc = cur / dp1;
   const int rc = (int)(cur - pc * dp1);
+  if (npi && (int)(pc / (uint32_t)npi) != img) return false;
   bool eq = true;
 #pragma unroll
   for (int a = 0; a < MD; a++)
@@ -197,7 +206,7 @@ __device__ __forceinline__ bool same_vertex(uint32_t cur, const int16_t (&key)[M
 
 template <int D>
 __global__ void __launch_bounds__(kThreads)
-    k_insert(int Npad, int d_rt, const int16_t* __restrict__ rem, const uint8_t* __restrict__ rnk,
+    k_insert(int Npad, int d_rt, int npi, const int16_t* __restrict__ rem, const uint8_t* __restrict__ rnk,
              uint32_t* __restrict__ table, uint32_t mask, uint32_t* __restrict__ slot_of) {
   constexpr int MD = D ? D : kMaxFeatureDims;
   const int d = D ? D : d_rt;
@@ -206,6 +215,7 @@ __global__ void __launch_bounds__(kThreads)
   const unsigned vmask = __ballot_sync(0xffffffffu, valid);
   if (!valid) return;
   const int lane = threadIdx.x & 31;
+  const int img = npi ? i / npi : 0;
 
   int16_t r0[MD];
   int rk[MD];
@@ -221,13 +231,14 @@ __global__ void __launch_bounds__(kThreads)
 #pragma unroll
     for (int a = 0; a < MD; a++)
       if (a < d) key[a] = key_coord(r0[a], rk[a], r, d);
-    const uint64_t h = hash_key<MD>(key, d);
+    uint64_t h = hash_key<MD>(key, d);
+    if (npi) h = hash_img(h, img);
     const uint32_t t = (uint32_t)i * (uint32_t)(d + 1) + (uint32_t)r;
 
     // warp aggregation: neighbouring pixels mostly share vertices; one lane per distinct key probes
     const unsigned peers = __match_any_sync(vmask, h);
     const int leader = __ffs(peers) - 1;
-    bool same = true;
+    bool same = __shfl_sync(peers, img, leader) == img;
 #pragma unroll
     for (int a = 0; a < MD; a++)
       if (a < d) same &= (__shfl_sync(peers, (int)key[a], leader) == (int)key[a]);
@@ -241,7 +252,7 @@ __global__ void __launch_bounds__(kThreads)
           cur = atomicCAS(table + slot, kEmpty, t);
           if (cur == kEmpty) break;  // claimed an empty slot: we are (for now) its representative
         }
-        if (same_vertex<MD>(cur, key, d, rem, rnk)) {
+        if (same_vertex<MD>(cur, key, d, rem, rnk, npi, img)) {
           if (t < cur) atomicMin(table + slot, t);
           break;
         }
@@ -266,7 +277,8 @@ __global__ void __launch_bounds__(kThreads)
     k_assign(uint32_t T, uint32_t E, int d_rt, const uint32_t* __restrict__ table, const uint32_t* __restrict__ slot_of,
              const int* __restrict__ vidx, const float* __restrict__ bary, const int16_t* __restrict__ rem,
              const uint8_t* __restrict__ rnk, PixEntry* __restrict__ pix, uint32_t* __restrict__ sort_key,
-             uint32_t* __restrict__ sort_val, int* __restrict__ count, int16_t* __restrict__ keys) {
+             uint32_t* __restrict__ sort_val, int* __restrict__ count, int16_t* __restrict__ keys, int npi,
+             int* __restrict__ vimg) {
   constexpr int MD = D ? D : kMaxFeatureDims;
   const int d = D ? D : d_rt;
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -288,6 +300,7 @@ __global__ void __launch_bounds__(kThreads)
 #pragma unroll
     for (int a = 0; a < MD; a++)
       if (a < d) keys[(size_t)vid * d + a] = key_coord(rem[(size_t)pc * d + a], rnk[(size_t)pc * d + a], rc, d);
+    if (npi) vimg[vid] = (int)(pc / (uint32_t)npi);
   }
 }
 
@@ -328,12 +341,14 @@ __global__ void k_max_int(int n, const int* __restrict__ a, int* __restrict__ ou
 
 template <int MD>
 __device__ __forceinline__ int lookup(const int16_t (&key)[MD], int d, const uint32_t* __restrict__ table,
-                                      uint32_t mask, const int16_t* __restrict__ keys) {
-  uint32_t slot = (uint32_t)hash_key<MD>(key, d) & mask;
+                                      uint32_t mask, const int16_t* __restrict__ keys, const int* __restrict__ vimg, int img) {
+  uint64_t h = hash_key<MD>(key, d);
+  if (vimg) h = hash_img(h, img);
+  uint32_t slot = (uint32_t)h & mask;
   for (;;) {
     const uint32_t cur = __ldg(table + slot);
     if (cur == kEmpty) return -1;
-    bool eq = true;
+    bool eq = !vimg || __ldg(vimg + cur) == img;
 #pragma unroll
     for (int a = 0; a < MD; a++)
       if (a < d) eq &= (__ldg(keys + (size_t)cur * d + a) == key[a]);
@@ -347,12 +362,13 @@ __device__ __forceinline__ int lookup(const int16_t (&key)[MD], int d, const uin
 template <int D>
 __global__ void __launch_bounds__(kThreads)
     k_neighbours(int V, int d_rt, const int16_t* __restrict__ keys, const uint32_t* __restrict__ table, uint32_t mask,
-                 int2* __restrict__ nbr) {
+                 const int* __restrict__ vimg, int2* __restrict__ nbr) {
   constexpr int MD = D ? D : kMaxFeatureDims;
   const int d = D ? D : d_rt;
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   const int j = blockIdx.y;
   if (v >= V) return;
+  const int img = vimg ? vimg[v] : 0;
   int16_t n1[MD], n2[MD];
 #pragma unroll
   for (int a = 0; a < MD; a++)
@@ -366,8 +382,8 @@ __global__ void __launch_bounds__(kThreads)
       }
     }
   int2 o;
-  o.x = lookup<MD>(n1, d, table, mask, keys) + 1;
-  o.y = lookup<MD>(n2, d, table, mask, keys) + 1;
+  o.x = lookup<MD>(n1, d, table, mask, keys, vimg, img) + 1;
+  o.y = lookup<MD>(n2, d, table, mask, keys, vimg, img) + 1;
   nbr[(size_t)j * V + v] = o;
 }
 
@@ -394,7 +410,7 @@ void build_impl(Ctx cx, const ElevateParams& ep, Lattice* L) {
   uint32_t* slot_of = dev_alloc<uint32_t>(T, s);
   {
     LaunchScope ls(cx.prof, s, "lattice_insert");
-    k_insert<D><<<blocks_for(Npad), kThreads, 0, s>>>(Npad, d, rem, rnk, table, (uint32_t)(cap - 1), slot_of);
+    k_insert<D><<<blocks_for(Npad), kThreads, 0, s>>>(Npad, d, ep.npi, rem, rnk, table, (uint32_t)(cap - 1), slot_of);
   }
 
   int* flag = dev_alloc<int>(T, s);
@@ -424,6 +440,7 @@ void build_impl(Ctx cx, const ElevateParams& ep, Lattice* L) {
   L->keys = dev_alloc<int16_t>((size_t)V * d, s);
   L->csr = dev_alloc<CsrEntry>(E, s);
   L->csr_start = dev_alloc<int>((size_t)V + 1, s);
+  if (ep.npi) L->vimg = dev_alloc<int>((size_t)V, s);
   L->nbr = dev_alloc<int2>((size_t)V * dp1, s);
 
   int* count = dev_alloc<int>((size_t)V + 2, s);
@@ -435,7 +452,7 @@ void build_impl(Ctx cx, const ElevateParams& ep, Lattice* L) {
   {
     LaunchScope ls(cx.prof, s, "lattice_assign");
     k_assign<D><<<blocks_for(T), kThreads, 0, s>>>(T, E, d, table, slot_of, vidx, bary, rem, rnk, L->pix, skey, sval,
-                                                   count, L->keys);
+                                                   count, L->keys, ep.npi, L->vimg);
     k_table_to_ids<<<blocks_for(T), kThreads, 0, s>>>(T, flag, vidx, slot_of, table);
   }
   {
@@ -476,7 +493,7 @@ void build_impl(Ctx cx, const ElevateParams& ep, Lattice* L) {
   if (V > 0) {
     LaunchScope ls(cx.prof, s, "lattice_neighbours");
     dim3 grid(blocks_for(V), dp1);
-    k_neighbours<D><<<grid, kThreads, 0, s>>>(V, d, L->keys, table, (uint32_t)(cap - 1), L->nbr);
+    k_neighbours<D><<<grid, kThreads, 0, s>>>(V, d, L->keys, table, (uint32_t)(cap - 1), L->vimg, L->nbr);
   }
   int* dmax = dev_alloc<int>(1, s);
   DCRF_CUDA(cudaMemsetAsync(dmax, 0, sizeof(int), s));
@@ -499,7 +516,9 @@ void Lattice::release(cudaStream_t s) {
   dev_free(nbr, s);
   dev_free(keys, s);
   dev_free(order, s);
+  dev_free(vimg, s);
   order = nullptr;
+  vimg = nullptr;
   pix = nullptr;
   csr_start = nullptr;
   csr = nullptr;
@@ -507,7 +526,7 @@ void Lattice::release(cudaStream_t s) {
   keys = nullptr;
 }
 
-void lattice_build(Ctx cx, const FeatureSource& src, int d, int N, Lattice* out) {
+void lattice_build(Ctx cx, const FeatureSource& src, int d, int N, Lattice* out, int npi) {
   DCRF_REQUIRE(d >= 1 && d <= kMaxFeatureDims,
                "feature dimension must be in [1, " + std::to_string(kMaxFeatureDims) + "], got " + std::to_string(d));
   DCRF_REQUIRE(N >= 1, "need at least one variable");
@@ -515,7 +534,9 @@ void lattice_build(Ctx cx, const FeatureSource& src, int d, int N, Lattice* out)
   ep.N = N;
   ep.Npad = (N + 3) & ~3;  // the reference walks pixels in blocks of 4 and inserts the padding lanes too
   ep.d = d;
+  ep.npi = npi;
   ep.src = src;
+  DCRF_REQUIRE(npi == 0 || (npi % 4 == 0 && N % npi == 0), "a batch needs images of a multiple of four pixels");
   DCRF_REQUIRE((uint64_t)ep.Npad * (uint64_t)(d + 1) < (1ull << 31), "nvar*(d+1) must stay below 2^31");
   // permutohedral.cpp:179-182: float inv_std_dev, scale evaluated in double then narrowed
   const float inv_std_dev = (float)(std::sqrt(2.0 / 3.0) * (double)(d + 1));

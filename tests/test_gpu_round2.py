@@ -135,3 +135,43 @@ def test_cuda_array_interface_probe_on_host_matrix():
     m = e.matrixXf(np.ones((3, 4), np.float32))
     assert not hasattr(m, "__cuda_array_interface__")   # AttributeError, not ValueError: hasattr-style probes work
     assert np.array(m).shape == (3, 4)
+
+
+def test_super_lattice_batch_equals_per_image_models(dcrf, monkeypatch):
+    """map_batch_2d runs chunks of images as one model whose lattices are the per-image lattices side by side (image index
+    = extra key coordinate).  Labels and Q must equal separate per-image models bit for bit: one chunk, several chunks of
+    uneven size, the per-image fallback (BATCH_MODE=0 and W*H % 4 != 0), different image content per slot."""
+    from tests import workloads as wl
+
+    W, H, L, B = 64, 48, 21, 7
+    U = np.stack([wl.softmax_unary(H, W, L, seed=b, grid=8) for b in range(B)])
+    I = np.stack([wl.smooth_image(H, W, seed=b, grid=8) if b % 3 else wl.noise_image(H, W, seed=b) for b in range(B)])
+    want_l, want_q = [], []
+    for b in range(B):
+        d = dcrf.DenseCRF2D(W, H, L)
+        d.setUnaryEnergy(U[b])
+        d.addPairwiseGaussian(sxy=3, compat=3)
+        d.addPairwiseBilateral(sxy=80, srgb=13, rgbim=I[b], compat=10)
+        Qb = d.inference(4)
+        want_q.append(np.array(Qb))
+        want_l.append(d.currentMap(Qb).copy())
+    for chunk, mode in (("0", "1"), ("3", "1"), ("2", "1"), ("0", "0")):
+        monkeypatch.setenv("DCRF_B200_BATCH_CHUNK", chunk)
+        monkeypatch.setenv("DCRF_B200_BATCH_MODE", mode)
+        lab, Q = dcrf.map_batch_2d(U, I, n_iter=4, return_q=True)
+        for b in range(B):
+            assert np.array_equal(Q[b], want_q[b]), (chunk, mode, b)
+            assert np.array_equal(lab[b].ravel(), want_l[b]), (chunk, mode, b)
+    monkeypatch.setenv("DCRF_B200_BATCH_CHUNK", "0")
+    monkeypatch.setenv("DCRF_B200_BATCH_MODE", "1")
+    # W*H not a multiple of four: the reference pads every image with phantom pixels, the batch path falls back
+    W2, H2 = 21, 13
+    U2 = np.stack([wl.softmax_unary(H2, W2, 5, seed=b, grid=4) for b in range(3)])
+    I2 = np.stack([wl.smooth_image(H2, W2, seed=b, grid=4) for b in range(3)])
+    lab2 = dcrf.map_batch_2d(U2, I2, n_iter=2)
+    for b in range(3):
+        d = dcrf.DenseCRF2D(W2, H2, 5)
+        d.setUnaryEnergy(U2[b])
+        d.addPairwiseGaussian(sxy=3, compat=3)
+        d.addPairwiseBilateral(sxy=80, srgb=13, rgbim=I2[b], compat=10)
+        assert np.array_equal(lab2[b].ravel(), d.currentMap(d.inference(2)))
