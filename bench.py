@@ -387,44 +387,52 @@ def run_b200(args):
     inputs = [Up] + [pinned_empty(U.shape, np.float32) for _ in range(n_thr - 1)]
     for b in inputs[1:]:
         b[...] = U
-    start = threading.Barrier(n_thr + 1)
     compute_lane = threading.Lock()
-    sums = [0.0] * n_thr
 
-    def pipe_worker(k):
-        m, uh = models[k], inputs[k]
-        q = Qd = None
-        for _ in range(4):                 # same pattern as the timed loop (two result matrices alive per model)
-            m.setUnaryEnergy(uh)
-            Qd = m.inference(N_ITER)
-            m.synchronize()
-            q = np.asarray(Qd)
-        start.wait()
-        for _ in range(args.steps):
-            m.setUnaryEnergy(uh)           # H2D on the model's stream; returns once enqueued
-            with compute_lane:             # one inference on the SMs at a time (two would evict each other's L2 lines)
+    def run_pipelined(fetch):
+        start = threading.Barrier(n_thr + 1)
+
+        def pipe_worker(k):
+            m, uh = models[k], inputs[k]
+            q = Qd = None
+            for _ in range(4):                 # same pattern as the timed loop (two result matrices alive per model)
+                m.setUnaryEnergy(uh)
                 Qd = m.inference(N_ITER)
                 m.synchronize()
-            q = np.asarray(Qd)             # D2H, overlaps the next thread's inference
-        sums[k] = float(q[0, 0])
+                q = fetch(Qd)
+            start.wait()
+            for _ in range(args.steps):
+                m.setUnaryEnergy(uh)           # H2D on the model's stream; returns once enqueued
+                with compute_lane:             # one inference on the SMs at a time (two would evict each other's L2 lines)
+                    Qd = m.inference(N_ITER)
+                    m.synchronize()
+                q = fetch(Qd)                  # D2H, overlaps the next thread's inference
+            del q
 
-    threads = [threading.Thread(target=pipe_worker, args=(k,)) for k in range(n_thr)]
-    for t in threads:
-        t.start()
-    barrier(dist, torch)
-    start.wait()
-    t_0 = time.perf_counter()
-    for t in threads:
-        t.join()
-    p_ms = (time.perf_counter() - t_0) * 1e3
-    barrier(dist, torch)
-    p_ms = max_over_ranks(p_ms, dist, torch, local) / (args.steps * n_thr)
+        threads = [threading.Thread(target=pipe_worker, args=(k,)) for k in range(n_thr)]
+        for t in threads:
+            t.start()
+        barrier(dist, torch)
+        start.wait()
+        t_0 = time.perf_counter()
+        for t in threads:
+            t.join()
+        p = (time.perf_counter() - t_0) * 1e3
+        barrier(dist, torch)
+        return max_over_ranks(p, dist, torch, local) / (args.steps * n_thr)
+
     if n_thr > 1:
+        p_ms = run_pipelined(np.asarray)
+        p_ms_map = run_pipelined(lambda Qm: np.argmax(Qm, axis=0))
         e2e["pipelined"] = {"host_threads": n_thr, "ms_per_step": p_ms,
                             "value": world * N * N_ITER / (p_ms * 1e-3) / 1e6,
                             "note": "same per-step API calls and bytes as e2e.value, issued from %d host threads with one "
                                     "model (own stream) each and a lock around inference, so that the copies of one step "
-                                    "overlap the kernels of another; throughput, not latency" % n_thr}
+                                    "overlap the kernels of another; throughput, not latency" % n_thr,
+                            "map_output": {"ms_per_step": p_ms_map, "value": world * N * N_ITER / (p_ms_map * 1e-3) / 1e6,
+                                           "note": "same, with np.argmax(inference(10), axis=0): the label map (4 MB) comes back "
+                                                   "instead of Q (174 MB).  Device->host is the direction that saturates first "
+                                                   "when several ranks share a host (profiles/r02g_pcie_4gpu.txt)"}}
     del models[1:], inputs[1:]
 
     # ---- per-kernel durations: same steps, every launch bracketed by CUDA events ---------------------

@@ -179,6 +179,10 @@ void dcrf_mat_release_host(dcrf_mat_t* a);
  * DMA at full PCIe rate (pageable ones are staged by the driver at a fraction of it).  These two hand out
  * and take back page-locked blocks from the library's pool (pydensecrf_b200.utils.pinned_empty wraps them). */
 dcrf_status dcrf_host_alloc(size_t bytes, void** out);
+/* The library keeps freed device buffers (result matrices, batch slabs; up to 48 GB), page-locked host buffers (up to
+ * 8 GB) and the stream-ordered pool's memory for reuse.  This returns all of it that is not in use to the driver
+ * (the same happens automatically when a device allocation fails). */
+void dcrf_empty_cache(void);
 void dcrf_host_free(void* p, size_t bytes);
 
 /* ---- measurement (bench.py) ------------------------------------------------------------------- */

@@ -79,6 +79,7 @@ cdef extern from "dcrf_b200.h" nogil:
     int dcrf_set_softmax_mode(dcrf_t* m, int fast)
     int dcrf_set_kernel_variant(dcrf_t* m, int mask)
     int dcrf_set_kl_mode(dcrf_t* m, int mode)
+    void dcrf_empty_cache()
     int dcrf_set_matrix_mode(dcrf_t* m, int mode)
     int dcrf_host_alloc(size_t nbytes, void** out)
     void dcrf_host_free(void* p, size_t nbytes)
@@ -416,6 +417,11 @@ cdef class LogisticUnary(Unary):
         self._u = L.copy()
         self._f = f.copy()
         self._logistic = True
+
+
+def empty_cache():
+    """Give the library's cached device buffers, page-locked host buffers and memory-pool reserves back to the driver."""
+    dcrf_empty_cache()
 
 
 def map_batch_2d(float[:, :, ::1] unaries not None, unsigned char[:, :, :, ::1] images not None, sxy_gaussian=3,

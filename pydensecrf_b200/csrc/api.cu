@@ -23,6 +23,7 @@
 namespace dcrf {
 
 static thread_local std::string g_last_error;
+thread_local Arena* t_arena = nullptr;
 
 void fail_cuda(cudaError_t e, const char* expr, const char* file, int line) {
   cudaGetLastError();  // clear sticky-less errors
@@ -30,6 +31,30 @@ void fail_cuda(cudaError_t e, const char* expr, const char* file, int line) {
   throw Error(e == cudaErrorMemoryAllocation ? DCRF_ENOMEM : DCRF_ECUDA,
               std::string("CUDA error: ") + cudaGetErrorString(e) + " [" + expr + "] at " + (base ? base + 1 : file) +
                   ":" + std::to_string(line));
+}
+
+// ---- private stream-ordered pools, one per device ------------------------------------------------------
+static std::mutex& g_pool_mu = *new std::mutex();
+static cudaMemPool_t g_pools[64] = {};
+cudaMemPool_t device_pool() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (g_pools[dev]) return g_pools[dev];
+  std::lock_guard<std::mutex> g(g_pool_mu);
+  if (!g_pools[dev]) {
+    cudaMemPoolProps props{};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    cudaMemPool_t pool = nullptr;
+    DCRF_CUDA(cudaMemPoolCreate(&pool, &props));
+    uint64_t keep = UINT64_MAX;  // keep freed blocks cached: no driver calls in steady state (dcrf_empty_cache trims)
+    DCRF_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    g_pools[dev] = pool;
+  }
+  return g_pools[dev];
 }
 
 // ---- profiler ----------------------------------------------------------------------------------
@@ -101,6 +126,12 @@ struct PinnedPool {
     free_blocks.emplace(bytes, p);
     cached += bytes;
   }
+  void trim() {
+    std::lock_guard<std::mutex> g(mu);
+    for (auto& b : free_blocks) cudaFreeHost(b.second);
+    free_blocks.clear();
+    cached = 0;
+  }
 };
 static PinnedPool g_pinned;
 
@@ -110,7 +141,7 @@ struct DevicePool {
   std::mutex mu;
   std::multimap<std::pair<int, size_t>, void*> free_blocks;
   size_t cached = 0;
-  static constexpr size_t kMaxCached = 16ull << 30;
+  static constexpr size_t kMaxCached = 48ull << 30;
   void* get(int device, size_t bytes) {
     {
       std::lock_guard<std::mutex> g(mu);
@@ -123,7 +154,17 @@ struct DevicePool {
       }
     }
     void* p = nullptr;
-    DCRF_CUDA(cudaMalloc(&p, bytes ? bytes : 1));
+    cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+    if (e == cudaErrorMemoryAllocation) {  // give the cached blocks back to the driver and try once more
+      cudaGetLastError();
+      trim(device);
+      e = cudaMalloc(&p, bytes ? bytes : 1);
+    }
+    if (e == cudaErrorMemoryAllocation) {
+      cudaGetLastError();
+      throw Error(DCRF_ENOMEM, "out of device memory allocating " + std::to_string(bytes) + " bytes");
+    }
+    if (e != cudaSuccess) fail_cuda(e, "cudaMalloc", __FILE__, __LINE__);
     return p;
   }
   void put(int device, void* p, size_t bytes) {
@@ -135,8 +176,48 @@ struct DevicePool {
     free_blocks.emplace(std::make_pair(device, bytes), p);
     cached += bytes;
   }
+  // free every cached block of `device` (-1: all devices) and trim that device's stream-ordered pool
+  void trim(int device) {
+    std::vector<std::pair<int, void*>> drop;
+    {
+      std::lock_guard<std::mutex> g(mu);
+      for (auto it = free_blocks.begin(); it != free_blocks.end();) {
+        if (device < 0 || it->first.first == device) {
+          drop.emplace_back(it->first.first, it->second);
+          cached -= it->first.second;
+          it = free_blocks.erase(it);
+        } else {
+          ++it;
+        }
+      }
+    }
+    int prev = -1;
+    cudaGetDevice(&prev);
+    for (auto& d : drop) {
+      cudaSetDevice(d.first);
+      cudaFree(d.second);
+    }
+    for (int dv = 0; dv < 64; dv++)
+      if ((device < 0 || dv == device) && g_pools[dv]) cudaMemPoolTrimTo(g_pools[dv], 0);
+    cudaGetLastError();
+    if (prev >= 0) cudaSetDevice(prev);
+  }
 };
 static DevicePool g_devpool;
+
+// arenas of the batch workers, recycled per (device, size) like the result buffers above
+struct ArenaScope {  // installs an arena for the calling thread (nullptr: suspends the current one) for a scope
+  Arena* prev;
+  explicit ArenaScope(Arena* a) : prev(t_arena) { t_arena = a; }
+  ~ArenaScope() { t_arena = prev; }
+};
+
+void trim_device_caches() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceSynchronize();  // frees queued on any stream have to have happened before the pool can give memory back
+  g_devpool.trim(dev);
+}
 
 struct DeviceGuard {
   int prev = -1;
@@ -323,10 +404,7 @@ dcrf_model* model_new(int N, int L, int W, int H, int device) {
   m->N = N, m->L = L, m->W = W, m->H = H, m->device = device;
   m->rl = RowLayout(L);
   DCRF_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
-  cudaMemPool_t pool;
-  DCRF_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-  uint64_t keep = UINT64_MAX;  // keep freed blocks cached: no driver calls in steady state
-  DCRF_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  device_pool();  // the library's own stream-ordered pool of this device
   DCRF_CUDA(cudaEventCreate(&m->t0));
   DCRF_CUDA(cudaEventCreate(&m->t1));
   m->kl_sums = dev_alloc<double>(3 + kl_partials(), m->stream);
@@ -847,6 +925,7 @@ std::shared_ptr<SharedLattice> shared_gaussian_lattice(dcrf_model* m, const Feat
     for (auto& e : g_geo_cache)
       if (e.first == key) return e.second;
   }
+  ArenaScope outside(nullptr);  // the shared lattice outlives the caller's chunk: never from a worker's arena
   auto sp = std::make_shared<SharedLattice>();
   sp->device = m->device;
   lattice_build(m->cx(), src, 2, m->N, &sp->lat, m->npi);
@@ -1449,6 +1528,13 @@ void dcrf_host_free(void* p, size_t bytes) {
 }
 
 // ---- measurement -----------------------------------------------------------------------------------
+void dcrf_empty_cache(void) {
+  try {
+    g_devpool.trim(-1);
+    g_pinned.trim();
+  } catch (...) {
+  }
+}
 dcrf_status dcrf_synchronize(dcrf_t* m) {
   return guarded([&] {
     DCRF_REQUIRE(m, "null argument");
@@ -1632,6 +1718,11 @@ struct BatchChunk {
   float* hq_ = nullptr;
 };
 
+// bytes one chunk may allocate: the N x Lp arrays (U, Q, two pre-scaled copies, value buffers of a lattice with up to
+// ~1.5 vertices per pixel), the lattice tables and the build scratch (hash table, sort buffers) -- a bound, not a need:
+// an allocation that does not fit falls through to the stream-ordered pool
+size_t chunk_arena_bytes(size_t N, int Lp) { return N * (600 + (size_t)Lp * 4 * 9) + (64u << 20); }
+
 // one chunk at a time owns a device's SMs (the kernels of two chunks would only evict each other's L2 lines); uploads
 // and the host-side delivery of other chunks run beside it
 std::mutex& device_lock(int dev) {
@@ -1689,12 +1780,34 @@ dcrf_status dcrf_batch_map_2d(int W, int H, int L, int device, int B, const floa
       const size_t N = (size_t)W * H;
       const int wk = next_worker.fetch_add(1);
       const int dev = (devices && n_devices > 0) ? devices[wk % n_devices] : device;
+      // super-lattice chunks allocate from a slab owned by this worker for the duration of the call (see Arena)
+      Arena arena;
+      int arena_dev = -1;
+      if (super) {
+        try {
+          arena_dev = pick_device(dev);
+          DeviceGuard g(arena_dev);
+          arena.cap = chunk_arena_bytes(N * (size_t)std::min(chunk, B), RowLayout(L).Lp);
+          arena.base = (char*)g_devpool.get(arena_dev, arena.cap);
+        } catch (...) {
+          arena = Arena();  // no slab: the chunks take the stream-ordered pool
+        }
+      }
+      struct ReturnSlab {
+        Arena& a;
+        int dev;
+        ~ReturnSlab() {
+          if (a.base) g_devpool.put(dev, a.base, a.cap);
+        }
+      } return_slab{arena, arena_dev};
       for (;;) {
         const int b = next.fetch_add(1);
         if (b >= nchunks || failed.load()) return;
         if (super) {
           const int b0 = b * chunk, Bc = std::min(chunk, B - b0);
           try {
+            arena.off = 0;  // the previous chunk of this worker is complete (its model synchronised and destroyed)
+            ArenaScope scope(arena.base ? &arena : nullptr);
             BatchChunk ch(bp, dev, b0, Bc);
             ch.upload(unary_LxN, rgb_HxWx3);
             {

@@ -45,22 +45,51 @@ struct RowLayout {
   bool seq() const { return L <= 2; }
 };
 
-// stream-ordered device memory (cudaMallocAsync pool with unlimited retention: steady-state
-// allocations inside inference cost no driver call)
+// A slab of device memory a batch worker hands out by bumping a pointer (api.cu: BatchChunk).  While a thread has an
+// arena installed, dev_alloc serves from it and dev_free of its pointers is a no-op; the slab is recycled as a whole when
+// the chunk is done.  A chunk of a batch makes ~40 allocations of up to a gigabyte with sizes that depend on the image
+// content; through the stream-ordered pool that meant fresh driver allocations for many calls (and seconds of them when
+// several processes grow their pools at once), through the arena it costs nothing.
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0, off = 0;
+  void* take(size_t bytes) {
+    const size_t o = (off + 255) & ~(size_t)255;
+    if (o + bytes > cap) return nullptr;
+    off = o + bytes;
+    return base + o;
+  }
+  bool owns(const void* p) const { return p >= (const void*)base && p < (const void*)(base + cap); }
+};
+extern thread_local Arena* t_arena;  // api.cu
+// the library's own stream-ordered pool of the calling thread's current device (created on first use; freed blocks stay
+// cached, so steady-state allocations cost no driver call).  The device's default pool, which other libraries in the
+// process may use, is left alone.
+cudaMemPool_t device_pool();
+void trim_device_caches();  // what dcrf_empty_cache does for the current device (called once before an allocation gives up)
+
+// stream-ordered device memory from device_pool()
 template <typename T>
 T* dev_alloc(size_t n, cudaStream_t s) {
   void* p = nullptr;
   if (n == 0) n = 1;
-  cudaError_t e = cudaMallocAsync(&p, n * sizeof(T), s);
+  if (t_arena && (p = t_arena->take(n * sizeof(T))) != nullptr) return static_cast<T*>(p);
+  cudaError_t e = cudaMallocFromPoolAsync(&p, n * sizeof(T), device_pool(), s);
+  if (e == cudaErrorMemoryAllocation) {  // return every cached block to the driver and try once more
+    cudaGetLastError();
+    trim_device_caches();
+    e = cudaMallocFromPoolAsync(&p, n * sizeof(T), device_pool(), s);
+  }
   if (e == cudaErrorMemoryAllocation) {
     cudaGetLastError();
     throw Error(DCRF_ENOMEM, "out of device memory allocating " + std::to_string(n * sizeof(T)) + " bytes");
   }
-  if (e != cudaSuccess) fail_cuda(e, "cudaMallocAsync", __FILE__, __LINE__);
+  if (e != cudaSuccess) fail_cuda(e, "cudaMallocFromPoolAsync", __FILE__, __LINE__);
   return static_cast<T*>(p);
 }
 inline void dev_free(void* p, cudaStream_t s) {
-  if (p) cudaFreeAsync(p, s);
+  if (!p || (t_arena && t_arena->owns(p))) return;
+  cudaFreeAsync(p, s);
 }
 
 // per-kernel-class profiling / launch accounting, owned by the model
