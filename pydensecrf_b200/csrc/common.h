@@ -181,7 +181,6 @@ struct Lattice {
   int16_t* keys = nullptr;     // [V*d]
   int* vimg = nullptr;         // [V] image index of every vertex (batched lattices only)
   float alpha = 1.f;           // 1/(1+2^-d)
-  int max_row = 0;             // longest CSR row (diagnostic)
   void release(cudaStream_t s);
 };
 

@@ -332,13 +332,6 @@ __global__ void k_order_keys(int V, const int* __restrict__ count, uint32_t* __r
   val[v] = (uint32_t)v;
 }
 
-__global__ void k_max_int(int n, const int* __restrict__ a, int* __restrict__ out) {
-  int m = 0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = max(m, a[i]);
-  for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0) atomicMax(out, m);
-}
-
 template <int MD>
 __device__ __forceinline__ int lookup(const int16_t (&key)[MD], int d, const uint32_t* __restrict__ table,
                                       uint32_t mask, const int16_t* __restrict__ keys, const int* __restrict__ vimg, int img) {
@@ -495,15 +488,12 @@ void build_impl(Ctx cx, const ElevateParams& ep, Lattice* L) {
     dim3 grid(blocks_for(V), dp1);
     k_neighbours<D><<<grid, kThreads, 0, s>>>(V, d, L->keys, table, (uint32_t)(cap - 1), L->vimg, L->nbr);
   }
-  int* dmax = dev_alloc<int>(1, s);
-  DCRF_CUDA(cudaMemsetAsync(dmax, 0, sizeof(int), s));
-  if (V > 0) k_max_int<<<128, kThreads, 0, s>>>(V, count, dmax);
-  DCRF_CUDA(cudaMemcpyAsync(&L->max_row, dmax, sizeof(int), cudaMemcpyDeviceToHost, s));
   DCRF_CUDA(cudaGetLastError());
-  DCRF_CUDA(cudaStreamSynchronize(s));
+  // no synchronisation here: the temporaries are freed in stream order and every caller synchronises once its term is
+  // complete (add_term)
 
   for (void* p : {(void*)bary, (void*)rem, (void*)rnk, (void*)table, (void*)slot_of, (void*)flag, (void*)vidx,
-                  (void*)count, (void*)skey, (void*)sval, (void*)skey2, (void*)sval2, (void*)dmax})
+                  (void*)count, (void*)skey, (void*)sval, (void*)skey2, (void*)sval2})
     dev_free(p, s);
 }
 
