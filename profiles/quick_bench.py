@@ -39,6 +39,7 @@ for mask in masks:
     if ref is None:
         ref = q
     same = bool(np.array_equal(q, ref))
-    print("%-28s order=%s mask=%d  %.3f ms  same_bits=%s  %s" % (
-        tag, "-", mask, ms, same,
+    import hashlib
+    print("%-28s q=%s mask=%d  %.3f ms  same_bits=%s  %s" % (
+        tag, hashlib.sha1(q.tobytes()).hexdigest()[:8], mask, ms, same,
         " ".join("%s=%.4f" % (k, v[1] / v[0]) for k, v in sorted(p.items()))), flush=True)
