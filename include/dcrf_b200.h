@@ -226,6 +226,14 @@ dcrf_status dcrf_lattice_dump(dcrf_t* m, int k, int32_t* offset, float* bary, in
 dcrf_status dcrf_lattice_filter(dcrf_t* m, int k, const float* in_NxL, int L, int reverse, float* out_NxL);
 /* PairwisePotential::apply of term k (pairwise.cpp:173-178) on a device matrix -> new matrix */
 dcrf_status dcrf_pairwise_apply(dcrf_t* m, int k, dcrf_mat_t* Q, dcrf_mat_t** out);
+/* ---- learning-path building blocks (not wrapped by densecrf.pyx, densecrf.pxd:61-76) ----------------------
+ * PairwisePotential::applyTranspose (pairwise.cpp:179-183): filter with the normalisations swapped and the blur axes in
+ * reverse order, then the (symmetric) compatibility. */
+dcrf_status dcrf_pairwise_apply_transpose(dcrf_t* m, int k, dcrf_mat_t* Q, dcrf_mat_t** out);
+/* Permutohedral::gradient (permutohedral.cpp:612-695) on term k's lattice: df[i*d + j] = d(a^T K b)/d feature j of
+ * variable i, for pixel-major a, b (N rows of L floats, the layout of MatrixXf::data()); df: N rows of d floats.
+ * DenseKernel::kernelGradient (pairwise.cpp:82-86) is exactly this call. */
+dcrf_status dcrf_lattice_gradient(dcrf_t* m, int k, const float* a_NxL, const float* b_NxL, int L, float* df_Nxd);
 /* 0 = pick automatically, 1 = force the staged (unfused) iteration, 2 = force the fused iteration (fails if
  * the model has a term the fused kernel cannot take) */
 dcrf_status dcrf_set_iteration_mode(dcrf_t* m, int mode);

@@ -380,6 +380,85 @@ static float orc_pexp_lane(float x0) {
   return (r > x0) ? r : x0; /* pmax(result, _x) */
 }
 
+/*
+ * Permutohedral::gradient (src/permutohedral.cpp:612-695): d/d(feature) of a^T K b.  For dir in {0,1}: splat a (dir 0) or
+ * b (dir 1); blur the axes ascending (dir 0) or descending (dir 1) with the scalar loop's arithmetic (0.5 is a double
+ * literal, :657); per pixel rotate the blurred corner values by the stored ranks (:660-672), multiply by the elevation
+ * matrix and dot with the other operand (:674-688).  df: N x d, pixel-major; a, b: N x vs.
+ */
+void orc_lattice_gradient(void *h, float *df, const float *a, const float *b, int vs) {
+  orc_lattice *lt = (orc_lattice *)h;
+  const int N = lt->N, d = lt->d, V = lt->V, dp = d + 1;
+  const size_t rows = (size_t)V + 2;
+  float *val = (float *)malloc(rows * vs * sizeof(float));
+  float *nxt = (float *)malloc(rows * vs * sizeof(float));
+  float *r_a = (float *)malloc(sizeof(float) * (size_t)dp * vs);
+  float *sm = (float *)malloc(sizeof(float) * (size_t)vs);
+  float scale[ORC_MAXD];
+  for (size_t e = 0; e < (size_t)N * d; e++) df[e] = 0.f;
+  const float inv_std_dev = (float)(sqrt(2.0 / 3.0) * (d + 1)); /* :623 */
+  for (int i = 0; i < d; i++) scale[i] = (float)(1.0 / sqrt((double)((i + 2) * (i + 1))) * inv_std_dev); /* :625 */
+  const float alpha = 1.0f / (1 + powf(2, -d)) / (d + 1); /* :629 */
+
+  for (int dir = 0; dir < 2; dir++) {
+    const float *in = dir ? b : a, *other = dir ? a : b;
+    for (size_t e = 0; e < rows * vs; e++) val[e] = nxt[e] = 0;
+    for (int i = 0; i < N; i++)
+      for (int j = 0; j <= d; j++) {
+        const size_t o = (size_t)lt->offset[(size_t)i * dp + j] + 1;
+        const float w = lt->bary[(size_t)i * dp + j];
+        for (int k = 0; k < vs; k++) {
+          float p = w * in[(size_t)i * vs + k];
+          val[o * vs + k] = val[o * vs + k] + p;
+        }
+      }
+    for (int j = dir ? d : 0; j <= d && j >= 0; dir ? j-- : j++) {
+      for (int v = 0; v < V; v++) {
+        const float *o = val + ((size_t)v + 1) * vs;
+        float *n = nxt + ((size_t)v + 1) * vs;
+        const float *n1 = val + ((size_t)lt->nbr[2 * ((size_t)j * V + v)] + 1) * vs;
+        const float *n2 = val + ((size_t)lt->nbr[2 * ((size_t)j * V + v) + 1] + 1) * vs;
+        for (int k = 0; k < vs; k++) n[k] = (float)((double)o[k] + 0.5 * (double)(n1[k] + n2[k]));
+      }
+      float *t = val;
+      val = nxt;
+      nxt = t;
+    }
+    for (int i = 0; i < N; i++) {
+      for (int e = 0; e < dp * vs; e++) r_a[e] = 0.f;
+      for (int j = 0; j <= d; j++) {
+        const int r0 = d - lt->rank[(size_t)i * dp + j];
+        const int r1 = r0 + 1 > d ? 0 : r0 + 1;
+        const size_t o0 = (size_t)lt->offset[(size_t)i * dp + r0] + 1;
+        const size_t o1 = (size_t)lt->offset[(size_t)i * dp + r1] + 1;
+        for (int k = 0; k < vs; k++) {
+          float p0 = alpha * val[o0 * vs + k];
+          r_a[j * vs + k] = r_a[j * vs + k] + p0;
+          float p1 = alpha * val[o1 * vs + k];
+          r_a[j * vs + k] = r_a[j * vs + k] - p1;
+        }
+      }
+      for (int k = 0; k < vs; k++) sm[k] = r_a[k];
+      for (int j = 1; j <= d; j++) {
+        float grad = 0;
+        for (int k = 0; k < vs; k++) {
+          float jr = (float)j * r_a[j * vs + k];
+          float df0 = sm[k] - jr;
+          float v = scale[j - 1] * df0;
+          float p = other[(size_t)i * vs + k] * v;
+          grad = grad + p;
+          sm[k] = sm[k] + r_a[j * vs + k];
+        }
+        df[(size_t)i * d + j - 1] = df[(size_t)i * d + j - 1] + grad;
+      }
+    }
+  }
+  free(val);
+  free(nxt);
+  free(r_a);
+  free(sm);
+}
+
 /* Eigen's linear vectorised sum over a 16-byte aligned float array
    (include/Eigen/src/Core/Redux.h:213-262 with Packet4f, predux at arch/SSE/PacketMath.h:540-551):
    two packet accumulators over 8-element strides, one optional trailing packet, horizontal add

@@ -78,6 +78,7 @@ class _Lib:
         self.lattice_nvert = fn("lattice_nvert", C.c_int, vp)
         self.lattice_dump = fn("lattice_dump", None, vp, _ip, _fp, _ip, _ip)
         self.lattice_filter = fn("lattice_filter", None, vp, _fp, _fp, C.c_int, C.c_int)
+        self.lattice_gradient = fn("lattice_gradient", None, vp, _fp, _fp, _fp, C.c_int)
         self.exp_and_normalize = fn("exp_and_normalize", None, _fp, _fp, C.c_int, C.c_int)
         self.crf_new = fn("crf_new", vp, C.c_int, C.c_int)
         self.crf_new_2d = fn("crf_new_2d", vp, C.c_int, C.c_int, C.c_int)
@@ -152,6 +153,18 @@ class Lattice:
         out = np.empty_like(x)
         self.lib.lattice_filter(self.h, _ptr(out), _ptr(x), x.shape[1], int(reverse))
         return out
+
+
+def _lattice_gradient(self, a_NxL, b_NxL):
+    """Permutohedral::gradient: (N, d) = d(a^T K b)/d(features) for (N, L) a, b."""
+    a, b = _f32(a_NxL), _f32(b_NxL)
+    assert a.shape == b.shape and a.shape[0] == self.N
+    df = np.zeros((self.N, self.d), np.float32)
+    self.lib.lattice_gradient(self.h, _ptr(df), _ptr(a), _ptr(b), a.shape[1])
+    return df
+
+
+Lattice.gradient = _lattice_gradient
 
 
 def exp_and_normalize(x_NxL, which="orc"):

@@ -89,6 +89,10 @@ void ref_lattice_filter(void* h, float* out_NxL, const float* in_NxL, int L, int
   std::memcpy(out_NxL, out.data(), sizeof(float) * (size_t)L * p->n());
 }
 
+void ref_lattice_gradient(void* h, float* df_Nxd, const float* a_NxL, const float* b_NxL, int L) {
+  static_cast<LatticeProbe*>(h)->gradient(df_Nxd, a_NxL, b_NxL, L);
+}
+
 void ref_exp_and_normalize(float* out_NxL, const float* in_NxL, int L, int N) {
   MatrixXf in = Eigen::Map<const MatrixXf>(in_NxL, L, N);
   MatrixXf out;

@@ -75,6 +75,8 @@ cdef extern from "dcrf_b200.h" nogil:
     int dcrf_lattice_dump(dcrf_t* m, int k, int32_t* offset, float* bary, int16_t* keys, int32_t* nbr, float* norm)
     int dcrf_lattice_filter(dcrf_t* m, int k, const float* inp, int L, int reverse, float* out)
     int dcrf_pairwise_apply(dcrf_t* m, int k, dcrf_mat_t* Q, dcrf_mat_t** out)
+    int dcrf_pairwise_apply_transpose(dcrf_t* m, int k, dcrf_mat_t* Q, dcrf_mat_t** out)
+    int dcrf_lattice_gradient(dcrf_t* m, int k, const float* a, const float* b, int L, float* df)
     int dcrf_set_iteration_mode(dcrf_t* m, int mode)
     int dcrf_set_softmax_mode(dcrf_t* m, int fast)
     int dcrf_set_kernel_variant(dcrf_t* m, int mask)
@@ -850,14 +852,30 @@ cdef class DenseCRF:
         _check(st)
         return out
 
-    def _pairwise_apply(self, int k, MatrixXf Q not None):
+    def _pairwise_apply(self, int k, MatrixXf Q not None, bint transpose=False):
+        """PairwisePotential::apply / applyTranspose of term k (pairwise.cpp:173-183)."""
         cdef dcrf_mat_t* o = NULL
         cdef dcrf_mat_t* q = Q.handle()
         cdef int st
+        cdef bint tr = transpose
         with nogil:
-            st = dcrf_pairwise_apply(self._h, k, q, &o)
+            st = dcrf_pairwise_apply_transpose(self._h, k, q, &o) if tr else dcrf_pairwise_apply(self._h, k, q, &o)
         _check(st)
         return MatrixXf()._adopt(o, self)
+
+    def _lattice_gradient(self, int k, float[:, ::1] a_NxL not None, float[:, ::1] b_NxL not None):
+        """Permutohedral::gradient of term k's lattice (permutohedral.cpp:612-695): (N, d) float32, d(a^T K b)/d features."""
+        import numpy as np
+        d, N, V = self._lattice_info(k)
+        if a_NxL.shape[0] != N or b_NxL.shape[0] != N or a_NxL.shape[1] != b_NxL.shape[1]:
+            raise ValueError("need two (N, L) inputs with N = {}".format(N))
+        out = np.empty((N, d), np.float32)
+        cdef float[:, ::1] o = out
+        cdef int L = <int>a_NxL.shape[1], st
+        with nogil:
+            st = dcrf_lattice_gradient(self._h, k, &a_NxL[0, 0], &b_NxL[0, 0], L, &o[0, 0])
+        _check(st)
+        return out
 
 
 cdef class DenseCRF2D(DenseCRF):

@@ -489,18 +489,23 @@ CompatDev compat_of(const Term* t) {
   return c;
 }
 
-// message of term k for the current Q into `out` (mode as in launch_slice): PairwisePotential::apply
-void term_apply(dcrf_model* m, Term* t, const float* Q, int mode, bool neg_unary, float* out) {
+// message of term k for the current Q into `out` (mode as in launch_slice): PairwisePotential::apply, or with
+// transpose = true PairwisePotential::applyTranspose (pairwise.cpp:179-183): the normalisations trade places, the blur
+// runs in reverse axis order (DenseKernel::filter, :63-80) and the compatibility is applied transposed -- which for
+// Potts, Diagonal and the symmetrised MatrixCompatibility is the same operator
+void term_apply(dcrf_model* m, Term* t, const float* Q, int mode, bool neg_unary, float* out, bool transpose = false) {
   Ctx cx = m->cx();
   ensure_val(m, t);
-  const float* fin = run_filter(cx, t->lat, m->rl, Q, t->pre() ? t->norm : nullptr, t->valA, t->valB);
+  const bool pre = t->ntype == DCRF_NORMALIZE_SYMMETRIC || t->ntype == (transpose ? DCRF_NORMALIZE_AFTER : DCRF_NORMALIZE_BEFORE);
+  const bool post = t->ntype == DCRF_NORMALIZE_SYMMETRIC || t->ntype == (transpose ? DCRF_NORMALIZE_BEFORE : DCRF_NORMALIZE_AFTER);
+  const float* fin = run_filter(cx, t->lat, m->rl, Q, pre ? t->norm : nullptr, t->valA, t->valB, transpose);
   if (t->ckind != DCRF_COMPAT_MATRIX) {
     CompatDev c = compat_of(t);
-    launch_slice(cx, t->lat, m->rl, fin, t->post() ? t->norm : nullptr, &c, mode, m->U, neg_unary, out);
+    launch_slice(cx, t->lat, m->rl, fin, post ? t->norm : nullptr, &c, mode, m->U, neg_unary, out);
   } else {
     ensure_scratch(m);
     DCRF_REQUIRE(out != m->msg, "internal: matrix term needs msg as scratch");
-    launch_slice(cx, t->lat, m->rl, fin, t->post() ? t->norm : nullptr, nullptr, SLICE_WRITE, nullptr, false, m->msg);
+    launch_slice(cx, t->lat, m->rl, fin, post ? t->norm : nullptr, nullptr, SLICE_WRITE, nullptr, false, m->msg);
     const bool tc = t->Whi && tc_wanted(m, t);
     if (tc)
       launch_matrix_compat_tc(cx, m->rl, m->N, t->Whi, t->Wlo, m->msg, mode, m->U, neg_unary, out);
@@ -1939,7 +1944,7 @@ dcrf_status dcrf_lattice_filter(dcrf_t* m, int k, const float* in_NxL, int L, in
     DCRF_CUDA(cudaStreamSynchronize(s));
   });
 }
-dcrf_status dcrf_pairwise_apply(dcrf_t* m, int k, dcrf_mat_t* Q, dcrf_mat_t** out) {
+static dcrf_status pairwise_apply_impl(dcrf_t* m, int k, dcrf_mat_t* Q, dcrf_mat_t** out, bool transpose) {
   if (!out) {
     g_last_error = "null argument";
     return DCRF_EINVAL;
@@ -1951,7 +1956,7 @@ dcrf_status dcrf_pairwise_apply(dcrf_t* m, int k, dcrf_mat_t* Q, dcrf_mat_t** ou
     float* q = mat_device(m, Q, true);
     a = new_result_mat(m);
     float* o = mat_device(m, a, false);
-    term_apply(m, m->terms[k], q, SLICE_WRITE, false, o);
+    term_apply(m, m->terms[k], q, SLICE_WRITE, false, o, transpose);
     DCRF_CUDA(cudaGetLastError());
     DCRF_CUDA(cudaEventRecord(Q->ready, m->stream));
     mat_written(m, a);
@@ -1962,6 +1967,39 @@ dcrf_status dcrf_pairwise_apply(dcrf_t* m, int k, dcrf_mat_t* Q, dcrf_mat_t** ou
   }
   *out = a;
   return DCRF_OK;
+}
+dcrf_status dcrf_pairwise_apply(dcrf_t* m, int k, dcrf_mat_t* Q, dcrf_mat_t** out) { return pairwise_apply_impl(m, k, Q, out, false); }
+dcrf_status dcrf_pairwise_apply_transpose(dcrf_t* m, int k, dcrf_mat_t* Q, dcrf_mat_t** out) {
+  return pairwise_apply_impl(m, k, Q, out, true);
+}
+dcrf_status dcrf_lattice_gradient(dcrf_t* m, int k, const float* a_NxL, const float* b_NxL, int L, float* df_Nxd) {
+  return guarded([&] {
+    DCRF_REQUIRE(m && k >= 0 && k < (int)m->terms.size(), "no such pairwise term");
+    DCRF_REQUIRE(a_NxL && b_NxL && df_Nxd && L >= 1 && L <= 4096, "bad argument");
+    DeviceGuard g(m->device);
+    Ctx cx = m->cx();
+    cudaStream_t s = m->stream;
+    const Lattice& lt = m->terms[k]->lat;
+    RowLayout rl(L);
+    const int N = lt.N;
+    float* rows[2];
+    const float* host[2] = {a_NxL, b_NxL};
+    for (int i = 0; i < 2; i++) {
+      float* packed = upload_tmp(m, host[i], (size_t)N * L * sizeof(float));
+      rows[i] = dev_alloc<float>((size_t)N * rl.Lp, s);
+      launch_unpack_rows(cx, rl, N, packed, rows[i]);
+      dev_free(packed, s);
+    }
+    const size_t vn = ((size_t)lt.V + 1) * rl.Lp;
+    float* A = dev_alloc<float>(vn, s);
+    float* B = dev_alloc<float>(vn, s);
+    float* df = dev_alloc<float>((size_t)N * lt.d, s);
+    lattice_gradient(cx, lt, rl, rows[0], rows[1], A, B, df);
+    DCRF_CUDA(cudaMemcpyAsync(df_Nxd, df, (size_t)N * lt.d * sizeof(float), cudaMemcpyDeviceToHost, s));
+    for (void* p : {(void*)rows[0], (void*)rows[1], (void*)A, (void*)B, (void*)df}) dev_free(p, s);
+    DCRF_CUDA(cudaGetLastError());
+    DCRF_CUDA(cudaStreamSynchronize(s));
+  });
 }
 dcrf_status dcrf_set_iteration_mode(dcrf_t* m, int mode) {
   return guarded([&] {

@@ -180,6 +180,8 @@ struct Lattice {
   int* order = nullptr;        // [V] splat work order: windows of 4096 vertex ids, inside a window by CSR row length
   int16_t* keys = nullptr;     // [V*d]
   int* vimg = nullptr;         // [V] image index of every vertex (batched lattices only)
+  uint8_t* rank = nullptr;     // [Npad*d] rank of the first d residuals of every pixel (rank_ of the reference; the last one
+                               // is what is missing from the permutation 0..d); read by the gradient only
   float alpha = 1.f;           // 1/(1+2^-d)
   void release(cudaStream_t s);
 };
@@ -195,7 +197,8 @@ void lattice_build(Ctx cx, const FeatureSource& src, int d, int N, Lattice* out,
 // out rows (V+1) x Lp.  `in` is N x Lp; pre_norm (may be null) scales row i by norm[i] first.
 void launch_splat(Ctx cx, const Lattice& lt, RowLayout rl, const float* in, const float* pre_norm, float* val);
 // one Jacobi blur pass along axis j: dst = src + 0.5*(src[n1] + src[n2])
-void launch_blur(Ctx cx, const Lattice& lt, RowLayout rl, int axis, const float* src, float* dst);
+// seq_math: seqCompute's arithmetic (0.5 as a double literal, permutohedral.cpp:505 / :657) whatever the channel count
+void launch_blur(Ctx cx, const Lattice& lt, RowLayout rl, int axis, const float* src, float* dst, bool seq_math = false);
 // axis `axis` then axis `axis2` in one launch (bit-identical to two launch_blur calls)
 void launch_blur2(Ctx cx, const Lattice& lt, RowLayout rl, int axis, int axis2, const float* src, float* dst);
 
@@ -276,6 +279,10 @@ void matrix_tc_dims(RowLayout rl, int* Np, int* Kp);
 void launch_split_w(Ctx cx, RowLayout rl, const float* W, float* hi, float* lo);
 void launch_matrix_compat_tc(Ctx cx, RowLayout rl, int N, const float* Bhi, const float* Blo, const float* msg, int mode,
                              const float* U, bool neg_unary, float* out);
+
+// Permutohedral::gradient (permutohedral.cpp:612-695), learn.cu: df (N x d, pixel-major, device) = d/df a^T K b for the
+// pixel-major N x Lp row arrays a and b; A and B are two zeroed (V+1) x Lp scratch buffers
+void lattice_gradient(Ctx cx, const Lattice& lt, RowLayout rl, const float* a, const float* b, float* A, float* B, float* df);
 
 // layout conversion at the boundary
 // batch > 1: `batch` images, each with its own (L, N) planes and N consecutive rows

@@ -492,7 +492,8 @@ void build_impl(Ctx cx, const ElevateParams& ep, Lattice* L) {
   // no synchronisation here: the temporaries are freed in stream order and every caller synchronises once its term is
   // complete (add_term)
 
-  for (void* p : {(void*)bary, (void*)rem, (void*)rnk, (void*)table, (void*)slot_of, (void*)flag, (void*)vidx,
+  L->rank = rnk;  // kept: Permutohedral::gradient reads rank_ (permutohedral.cpp:662)
+  for (void* p : {(void*)bary, (void*)rem, (void*)table, (void*)slot_of, (void*)flag, (void*)vidx,
                   (void*)count, (void*)skey, (void*)sval, (void*)skey2, (void*)sval2})
     dev_free(p, s);
 }
@@ -507,6 +508,8 @@ void Lattice::release(cudaStream_t s) {
   dev_free(keys, s);
   dev_free(order, s);
   dev_free(vimg, s);
+  dev_free(rank, s);
+  rank = nullptr;
   order = nullptr;
   vimg = nullptr;
   pix = nullptr;

@@ -177,6 +177,21 @@ def mid():
          ref_margin=(srt[-1] - srt[-2]).astype(np.float32), ref_Q_sub=Q[:, ::5].copy())
 
 
+def gradient():
+    """Permutohedral::gradient (permutohedral.cpp:612-695) from the reference on small lattices."""
+    rng = np.random.default_rng(17)
+    out = {}
+    cases = [(2, 60, 3), (5, 101, 21), (3, 9, 1), (4, 64, 2), (7, 40, 5)]
+    out["cases"] = np.array(cases, np.int32)
+    for ci, (d, N, L) in enumerate(cases):
+        f = (rng.standard_normal((d, N)) * 2.5).astype(np.float32)
+        a = rng.standard_normal((N, L)).astype(np.float32)
+        b = rng.random((N, L)).astype(np.float32)
+        out["f%d" % ci], out["a%d" % ci], out["b%d" % ci] = f, a, b
+        out["ref_df%d" % ci] = po.Lattice(f, "ref").gradient(a, b)
+    save("gradient.npz", **out)
+
+
 def _utils_cases():
     """Inputs for the utils goldens: (name, function name, args, kwargs)."""
     rng = np.random.default_rng(21)
@@ -230,3 +245,4 @@ if __name__ == "__main__":
     cfg1()
     mid()
     utils_golden()
+    gradient()

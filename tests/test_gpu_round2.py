@@ -175,3 +175,66 @@ def test_super_lattice_batch_equals_per_image_models(dcrf, monkeypatch):
         d.addPairwiseGaussian(sxy=3, compat=3)
         d.addPairwiseBilateral(sxy=80, srgb=13, rgbim=I2[b], compat=10)
         assert np.array_equal(lab2[b].ravel(), d.currentMap(d.inference(2)))
+
+
+@pytest.mark.parametrize("d,N,L", [(2, 700, 3), (5, 1001, 21), (5, 64, 1), (3, 257, 2), (7, 120, 5), (1, 40, 8), (9, 90, 4)])
+def test_lattice_gradient_exact(dcrf, oracle_built, d, N, L):
+    """Permutohedral::gradient (SURVEY 8f-4) on the device: same float operations in the same order as the reference's
+    scalar loops -> bit-equal to the oracle (which is pinned bit for bit against the reference, CPU tests)."""
+    rng = np.random.default_rng(d * 100 + N + L)
+    f = (rng.standard_normal((d, N)) * 2).astype(np.float32)
+    if N % 2 == 0:
+        f = np.round(f * 2) / 2      # ties: the stored ranks decide which corners a gradient entry combines
+    a = rng.standard_normal((N, L)).astype(np.float32)
+    b = rng.random((N, L)).astype(np.float32)
+    m = dcrf.DenseCRF(N, max(L, 1))
+    m.addPairwiseEnergy(np.ascontiguousarray(f), 1.0)
+    got = m._lattice_gradient(0, a, b)
+    want = oracle_built.Lattice(f, "orc").gradient(a, b)
+    assert got.shape == (N, d) and np.isfinite(got).all()
+    assert np.array_equal(got, want)
+
+
+def test_lattice_gradient_golden(dcrf):
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gradient.npz"))
+    for ci, (d, N, L) in enumerate(g["cases"]):
+        m = dcrf.DenseCRF(int(N), int(L))
+        m.addPairwiseEnergy(np.ascontiguousarray(g["f%d" % ci]), 1.0)
+        assert np.array_equal(m._lattice_gradient(0, g["a%d" % ci], g["b%d" % ci]), g["ref_df%d" % ci])
+
+
+@pytest.mark.parametrize("nt", [0, 1, 2, 3])
+@pytest.mark.parametrize("L", [2, 21])
+def test_pairwise_apply_transpose(dcrf, oracle_built, nt, L):
+    """PairwisePotential::applyTranspose (pairwise.cpp:179-183): normalisations swapped, blur axes in reverse order, Potts
+    compatibility; expected value composed from the oracle's own pieces (reverse filter, norm vector)."""
+    po = oracle_built
+    rng = np.random.default_rng(nt * 10 + L)
+    N, d, w = 600, 4, 2.5
+    f = (rng.standard_normal((d, N)) * 1.5).astype(np.float32)
+    Q = rng.random((L, N)).astype(np.float32)
+    import pydensecrf_b200.eigen as eigen
+
+    m = dcrf.DenseCRF(N, L)
+    m.addPairwiseEnergy(np.ascontiguousarray(f), w, normalization=dcrf.NormalizationType(nt))
+    o = po.CRF(N, L, "orc")
+    o.addPairwiseEnergy(f, w, normalization=nt)
+    norm = np.zeros(N, np.float32)
+    o.lib.crf_term_norm(o.h, 0, norm.ctypes.data_as(po._fp))
+    x = np.ascontiguousarray(Q.T)                       # (N, L) pixel-major
+    pre = nt == 3 or nt == 2                            # transpose: SYMMETRIC or AFTER scale the input
+    post = nt == 3 or nt == 1
+    if pre:
+        x = x * norm[:, None]
+    y = po.Lattice(f, "orc").filter(x, reverse=True)
+    if post:
+        y = y * norm[:, None]
+    want = (np.float32(-w) * y).T
+    got = np.array(m._pairwise_apply(0, eigen.matrixXf(Q), transpose=True))
+    assert np.array_equal(got, want)
+    fwd = np.array(m._pairwise_apply(0, eigen.matrixXf(Q)))
+    out = np.zeros((N, L), np.float32)
+    o.lib.crf_term_apply(o.h, 0, out.ctypes.data_as(po._fp), np.ascontiguousarray(Q.T).ctypes.data_as(po._fp))
+    assert np.array_equal(fwd, out.T)

@@ -127,3 +127,12 @@ def test_mid(oracle_built):
     Q = c.inference(10)
     assert np.array_equal(Q[:, ::5], g["ref_Q_sub"])
     assert np.array_equal(np.argmax(Q, 0), g["ref_MAP"])
+
+
+def test_lattice_gradient_matches_reference_golden(oracle_built):
+    """Permutohedral::gradient (learning path, SURVEY 8f-4): the restatement against vectors the reference produced."""
+    po = oracle_built
+    g = np.load(os.path.join(G, "gradient.npz"))
+    for ci, (d, N, L) in enumerate(g["cases"]):
+        lt = po.Lattice(g["f%d" % ci], "orc")
+        assert np.array_equal(lt.gradient(g["a%d" % ci], g["b%d" % ci]), g["ref_df%d" % ci]), (d, N, L)

@@ -26,6 +26,18 @@ def test_lattice_bit_exact(po, d, N):
             assert np.array_equal(a.filter(x, rev), b.filter(x, rev)), (L, rev)
 
 
+@pytest.mark.parametrize("d,N,L", [(2, 500, 3), (5, 333, 21), (5, 64, 1), (3, 100, 2), (8, 120, 4), (1, 40, 7)])
+def test_lattice_gradient_bit_exact(po, d, N, L):
+    """Permutohedral::gradient (permutohedral.cpp:612-695), incl. features with ties (ranks decide the rotation)."""
+    rng = np.random.default_rng(d * 100 + N + L)
+    f = (rng.standard_normal((d, N)) * 2).astype(np.float32)
+    if N % 2 == 0:
+        f = np.round(f * 2) / 2
+    a = rng.standard_normal((N, L)).astype(np.float32)
+    b = rng.random((N, L)).astype(np.float32)
+    assert np.array_equal(po.Lattice(f, "orc").gradient(a, b), po.Lattice(f, "ref").gradient(a, b))
+
+
 def test_lattice_ties_and_integers(po):
     """features on exact lattice positions exercise rank ties and round-half-even."""
     rng = np.random.default_rng(5)
