@@ -10,7 +10,7 @@ name, defs = sys.argv[1], sys.argv[2:]
 out = os.path.join(ROOT, "build", "variants", name)
 os.makedirs(out, exist_ok=True)
 objs = []
-for n in ("lattice", "filter", "filter_wide", "matrix_tc", "learn", "api"):
+for n in ("lattice", "filter", "filter_wide", "matrix_tc", "matrix_tc_tma", "learn", "api"):
     src, obj = os.path.join(g.CSRC, n + ".cu"), os.path.join(out, n + ".o")
     if n in os.environ.get("VARIANT_SRC", "filter,filter_wide").split(",") and defs:
         subprocess.check_call(["nvcc"] + g.NVCC_FLAGS + defs + ["-c", src, "-o", obj])

@@ -272,6 +272,10 @@ struct TCUArgs {
 };
 bool update_matrix_tc_supported(RowLayout rl, int nterms);
 void launch_update_matrix_tc(Ctx cx, RowLayout rl, TCUArgs a);
+// the same update fed by TMA with a thread-per-row epilogue out of TMEM (matrix_tc_tma.cu); launch_update_matrix_tc
+// dispatches to it when it is supported
+bool update_matrix_tc_tma_supported(RowLayout rl, int nterms);
+void launch_update_matrix_tc_tma(Ctx cx, RowLayout rl, TCUArgs a);
 
 // tensor-core (tcgen05, 3xTF32) MatrixCompatibility (matrix_tc.cu)
 bool matrix_tc_supported(RowLayout rl);

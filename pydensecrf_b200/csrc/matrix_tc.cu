@@ -810,7 +810,7 @@ bool matrix_tc_supported(RowLayout rl) { return rl.vec == 4 && rl.L >= 16 && rl.
 
 void matrix_tc_dims(RowLayout rl, int* Np, int* Kp) {
   *Np = (rl.Lp + 15) & ~15;             // UMMA N: multiple of 16 for M = 128
-  *Kp = ((rl.Lp + kKS - 1) / kKS) * kKS;  // whole slabs
+  *Kp = (rl.Lp + 31) & ~31;               // whole slabs of 32 (the TMA kernel's; two of this file's 16-wide ones)
 }
 
 void launch_split_w(Ctx cx, RowLayout rl, const float* W, float* hi, float* lo) {
@@ -846,6 +846,10 @@ bool update_matrix_tc_supported(RowLayout rl, int nterms) {
 }
 
 void launch_update_matrix_tc(Ctx cx, RowLayout rl, TCUArgs a) {
+  if (update_matrix_tc_tma_supported(rl, a.nterms)) {  // TMA-fed, thread-per-row epilogue (matrix_tc_tma.cu)
+    launch_update_matrix_tc_tma(cx, rl, a);
+    return;
+  }
   LaunchScope ls(cx.prof, cx.stream, "update_matrix_tc");
   a.L = rl.L, a.Lp = rl.Lp;
   matrix_tc_dims(rl, &a.Np, &a.Kp);

@@ -1,0 +1,470 @@
+// The mean-field update of models whose terms all carry a MatrixCompatibility, TMA-fed (round 2):
+//   Q = softmax( -U - sum_k W_k * msg_k )        (labelcompatibility.cpp:82-84, densecrf.cpp:98-106,123-127 in
+//                                                  /root/reference/pydensecrf/densecrf/src)
+// Same mathematics as k_update_matrix_tc_ws (matrix_tc.cu): per 128-pixel tile all terms' GEMMs accumulate into one TMEM
+// accumulator (3xTF32: hi*hi + lo*hi + hi*lo, fp32 accumulation), the epilogue forms x = (-U) - acc and runs the
+// bit-faithful column softmax.  What changed is who moves the data and who owns a row:
+//
+//   warp 0   (one lane)  TMA producer: per K slab of 32 floats one cp.async.bulk.tensor for the message tile (128 rows x
+//                        128 bytes) and one each for tf32(W) and W - tf32(W) (Np rows x 128 bytes), SWIZZLE_128B, landing on
+//                        an mbarrier with expect-tx; rows past N and columns past Lp are zero-filled by the TMA unit.
+//   warps 4-7            split the message slab in place into hi = tf32(x) and lo = x - hi (the only operand work left on
+//                        the SM: 8 float4 per thread and slab).
+//   warp 1   (one lane)  issues the 12 tcgen05.mma of a slab (4 k-steps x 3 products, descriptors advance 32 bytes inside
+//                        the swizzle atom) and commits them to the stage's "empty" barrier / the accumulator's "full" one.
+//   warps 8-15           epilogue, ONE THREAD PER PIXEL ROW straight out of TMEM (tcgen05.ld 32x32b: lane = row), two sets
+//                        of four warps taking alternate tiles so a set has two tile times for its row.  Row maximum, the
+//                        eight Eigen reduction chains and the shared reciprocal are thread-local: no shuffles, no
+//                        shared-memory tile.  The row lives in TMEM between the passes (x, then exp(x - max), written back
+//                        with tcgen05.st), so the registers hold 16 columns at a time; arithmetic is packed (FFMA2) with
+//                        the opaque-constant identities of packed_math.cuh.
+// The accumulator is double-buffered in TMEM (2 x 256 columns): tile t+1's main loop runs under tile t's epilogue.
+#include <cuda.h>  // CUtensorMap and the encoder's signature only; the entry point comes from cudaGetDriverEntryPoint
+
+#include <cstdlib>
+#include <type_traits>
+
+#include "common.h"
+#include "packed_math.cuh"
+#include "softmax_math.cuh"
+
+namespace dcrf {
+namespace {
+
+constexpr int kTM = 128;        // pixels per tile = UMMA M
+constexpr int kKB = 32;         // floats per K slab: one 128-byte swizzle row
+constexpr int kThreads = 512;   // 16 warps: 0 TMA, 1 MMA, 2 TMEM allocation, 4-7 split, 8-15 epilogue
+constexpr int kSplitWarp0 = 4, kSplitThreads = 128;
+constexpr int kEpiWarp0 = 8;
+constexpr int kMaxStages = 4;
+
+struct TmaMaps {
+  CUtensorMap a[kMaxTCUTerms], bhi[kMaxTCUTerms], blo[kMaxTCUTerms];
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, 0x989680;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t}\n"
+        : "=r"(done)
+        : "r"(mbar), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t mbar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+// one 2-D tile: coordinates (c0 = element along the row, c1 = row), completes `bytes of the box` on the mbarrier
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t mbar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(mbar)
+      : "memory");
+}
+// shared-memory matrix descriptor, K-major, SWIZZLE_128B: rows of 128 bytes, 8-row groups 1024 bytes apart (SBO),
+// LBO unused for swizzled K-major operands, version 1 (Blackwell), layout type 2 in bits [61,64)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "l"(a), "l"(b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t mbar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  uint32_t h;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+  hi = __uint_as_float(h);
+  lo = x - hi;  // exact
+}
+
+struct TmaArgs {
+  TCUArgs a;
+  int nstages;
+  float c_one, c_nzero, c_mone;  // 1, -0, -1 behind the kernel-argument curtain (packed_math.cuh)
+};
+
+__global__ void __launch_bounds__(kThreads, 1) k_update_matrix_tc_tma(const __grid_constant__ TmaMaps maps, const TmaArgs ta) {
+  extern __shared__ uint8_t smem_raw[];
+  const TCUArgs& a = ta.a;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int S = ta.nstages;
+  // SWIZZLE_128B wants the stage bases on 1024-byte boundaries of the shared window
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw);
+  const uint32_t szA = kTM * 128, szB = (uint32_t)a.Np * 128;
+  const uint32_t stage_bytes = 2 * szA + 2 * szB;  // [A -> A_hi][A_lo][B_hi][B_lo]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + (size_t)S * stage_bytes);
+  // bars: full[S] (TMA landed), split[S] (A_hi / A_lo ready), empty[S] (MMAs done reading), accfull[2], accempty[2]
+  const uint32_t b_full = smem_u32(bars), b_split = b_full + 8 * kMaxStages, b_empty = b_split + 8 * kMaxStages,
+                 b_accfull = b_empty + 8 * kMaxStages, b_accempty = b_accfull + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kMaxStages + 4);
+
+  if (tid == 0) {
+    for (int s = 0; s < S; s++) {
+      mbar_init(b_full + 8 * s, 1);
+      mbar_init(b_split + 8 * s, kSplitThreads);
+      mbar_init(b_empty + 8 * s, 1);
+    }
+    for (int b = 0; b < 2; b++) {
+      mbar_init(b_accfull + 8 * b, 1);
+      mbar_init(b_accempty + 8 * b, 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+  const int ntiles = (a.N + kTM - 1) / kTM;
+  const int nslabs = a.Kp / kKB;         // per term
+  const int gslabs = nslabs * a.nterms;  // per tile
+
+  if (warp == 0) {
+    // ---------------- TMA producer ---------------------------------------------------------------------------------
+    if (lane == 0) {
+      int s = 0;
+      uint32_t round = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        int term = 0, slab = 0;
+        for (int g = 0; g < gslabs; g++) {
+          if (round > 0) mbar_wait(b_empty + 8 * s, (round - 1) & 1);
+          const uint32_t st = base + (uint32_t)s * stage_bytes, fb = b_full + 8 * s;
+          mbar_expect_tx(fb, szA + 2 * szB);
+          tma_load_2d(st, &maps.a[term], slab * kKB, tile * kTM, fb);
+          tma_load_2d(st + 2 * szA, &maps.bhi[term], slab * kKB, 0, fb);
+          tma_load_2d(st + 2 * szA + szB, &maps.blo[term], slab * kKB, 0, fb);
+          if (++slab == nslabs) slab = 0, term++;
+          if (++s == S) s = 0, round++;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issue ------------------------------------------------------------------------------------
+    if (lane == 0) {
+      // instruction descriptor: D fp32, A/B tf32, both K-major, N = Np, M = 128
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.Np >> 3) << 17) | ((uint32_t)(kTM >> 4) << 24);
+      int s = 0;
+      uint32_t round = 0, tl = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tl++) {
+        const uint32_t buf = tl & 1, acc = tmem + buf * 256;
+        if (tl >= 2) mbar_wait(b_accempty + 8 * buf, ((tl >> 1) - 1) & 1);  // drained by the epilogue two tiles ago
+        for (int g = 0; g < gslabs; g++) {
+          mbar_wait(b_full + 8 * s, round & 1);
+          mbar_wait(b_split + 8 * s, round & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t st = base + (uint32_t)s * stage_bytes;
+#pragma unroll
+          for (int ks = 0; ks < kKB / 8; ks++) {  // one k-step = 8 tf32 = 32 bytes inside the 128-byte swizzle row
+            const uint64_t ahi = umma_desc_sw128(st + ks * 32), alo = umma_desc_sw128(st + szA + ks * 32);
+            const uint64_t bhi = umma_desc_sw128(st + 2 * szA + ks * 32), blo = umma_desc_sw128(st + 2 * szA + szB + ks * 32);
+            umma_tf32(acc, ahi, bhi, idesc, (g | ks) ? 1u : 0u);
+            umma_tf32(acc, alo, bhi, idesc, 1u);
+            umma_tf32(acc, ahi, blo, idesc, 1u);
+          }
+          umma_commit(b_empty + 8 * s);
+          if (g == gslabs - 1) umma_commit(b_accfull + 8 * buf);
+          if (++s == S) s = 0, round++;
+        }
+      }
+    }
+  } else if (warp >= kSplitWarp0 && warp < kSplitWarp0 + kSplitThreads / 32) {
+    // ---------------- message slab -> tf32 hi (in place) + lo ----------------------------------------------------------
+    const int t = tid - kSplitWarp0 * 32;
+    int s = 0;
+    uint32_t round = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int g = 0; g < gslabs; g++) {
+        mbar_wait(b_full + 8 * s, round & 1);
+        float4* A = reinterpret_cast<float4*>(sm + (size_t)s * stage_bytes);
+        float4* Alo = reinterpret_cast<float4*>(sm + (size_t)s * stage_bytes + szA);
+#pragma unroll
+        for (int i = 0; i < (int)(kTM * 128 / 16) / kSplitThreads; i++) {
+          const int e = t + i * kSplitThreads;
+          const float4 v = A[e];
+          float4 h, l;
+          split_tf32(v.x, h.x, l.x);
+          split_tf32(v.y, h.y, l.y);
+          split_tf32(v.z, h.z, l.z);
+          split_tf32(v.w, h.w, l.w);
+          A[e] = h;
+          Alo[e] = l;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA's async proxy
+        mbar_arrive(b_split + 8 * s);
+        if (++s == S) s = 0, round++;
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ---------------- epilogue: one thread per pixel row -----------------------------------------------------------------
+    const int set = (warp - kEpiWarp0) >> 2, q = warp & 3;  // a warp may touch the TMEM lanes 32 * (warp % 4) ..
+    const int L = a.L, Lp = a.Lp, nfull = L >> 2, ntail = L & 3;
+    const int lim4 = nfull * 4, lim8 = (nfull >> 1) * 8;
+    Pk c;
+    c.one = pk1(ta.c_one), c.nzero = pk1(ta.c_nzero), c.mone = pk1(ta.c_mone);
+    const u64 Z = pk1(a.neg_unary ? -0.f : 0.f);
+    uint32_t tl = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tl++) {
+      if ((int)(tl & 1) != set) continue;
+      const uint32_t buf = tl & 1;
+      const uint32_t tad = tmem + buf * 256 + ((uint32_t)(q * 32) << 16);
+      const int i = tile * kTM + q * 32 + lane;
+      const bool valid = i < a.N;
+      const float* urow = (a.U && valid) ? a.U + (size_t)i * Lp : nullptr;
+      float4 un[4];
+      auto load_u = [&](int c0) {
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+          un[j] = (urow && c0 + 4 * j < Lp) ? __ldg(reinterpret_cast<const float4*>(urow + c0 + 4 * j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      };
+      load_u(0);
+      mbar_wait(b_accfull + 8 * buf, (tl >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+      // Every pass walks the row in chunks of 16 columns; chunks that lie wholly inside the region a pass treats uniformly
+      // take the branch-free body (edge = false), the last one or two the general one.
+      // pass 1: x = (-U) - accumulator back into TMEM, row maximum and minimum
+      float mx = -INFINITY, mn = INFINITY;
+      auto pass1 = [&](int c0, auto edge_t) {
+        constexpr bool EDGE = decltype(edge_t)::value;
+        uint32_t r[16];
+        tmem_ld16(tad + c0, r);
+        float4 uc[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) uc[j] = un[j];
+        if (c0 + 16 < Lp) load_u(c0 + 16);
+        tmem_wait_ld();
+#pragma unroll
+        for (int p = 0; p < 8; p++) {
+          const int l = c0 + 2 * p;
+          const float4 u4 = uc[p >> 1];
+          const u64 up = (p & 1) ? pk2(u4.z, u4.w) : pk2(u4.x, u4.y);
+          const u64 x = sub2(sub2(Z, up, c), pk2(__uint_as_float(r[2 * p]), __uint_as_float(r[2 * p + 1])), c);
+          if (!EDGE || l + 1 < L) {
+            mx = fmaxf(mx, fmaxf(lo2(x), hi2(x)));
+            mn = fminf(mn, fminf(lo2(x), hi2(x)));
+          } else if (l < L) {
+            mx = fmaxf(mx, lo2(x));
+            mn = fminf(mn, lo2(x));
+          }
+          r[2 * p] = __float_as_uint(lo2(x)), r[2 * p + 1] = __float_as_uint(hi2(x));
+        }
+        tmem_st16(tad + c0, r);
+      };
+      int c0 = 0;
+      for (; c0 + 16 <= L; c0 += 16) pass1(c0, std::false_type());
+      for (; c0 < Lp; c0 += 16) pass1(c0, std::true_type());
+      tmem_wait_st();
+      // some exp(x - max) of this row is below the range the shared-reciprocal division is proven for (x - max is
+      // monotonic in x, so the row minimum decides)
+      const bool small = __fsub_rn(mn, mx) < -44.f;
+
+      // pass 2: e = exp(x - max) back into TMEM; Eigen's redux order: eight sequential chains over the packet pairs,
+      // p0 + p1, the odd trailing packet, (c0 + c2) + (c1 + c3), then the L % 4 tail one by one
+      const u64 MX = pk1(mx);
+      u64 ch[4] = {0ull, 0ull, 0ull, 0ull}, tp01 = 0ull, tp23 = 0ull;
+      float tx0 = 0.f, tx1 = 0.f, tx2 = 0.f;
+      auto pass2 = [&](int c0, auto edge_t) {
+        constexpr bool EDGE = decltype(edge_t)::value;
+        uint32_t r[16];
+        tmem_ld16(tad + c0, r);
+        tmem_wait_ld();
+#pragma unroll
+        for (int p = 0; p < 8; p++) {
+          const int l = c0 + 2 * p;
+          const u64 xs = sub2(pk2(__uint_as_float(r[2 * p]), __uint_as_float(r[2 * p + 1])), MX, c);
+          u64 e = 0ull;
+          if (!EDGE) {
+            e = eigen_pexp_nonpos2(xs, c);
+            ch[p & 3] = add2(ch[p & 3], e, c);
+          } else if (l < lim4) {
+            e = eigen_pexp_nonpos2(xs, c);
+            if (l < lim8) {
+              ch[p & 3] = add2(ch[p & 3], e, c);
+            } else if ((p & 3) == 0) {
+              tp01 = e;
+            } else if ((p & 3) == 1) {
+              tp23 = e;
+            }
+          } else if (l == lim4) {
+            tx0 = lo2(xs), tx1 = hi2(xs);
+          } else if (l == lim4 + 2) {
+            tx2 = lo2(xs);
+          }
+          r[2 * p] = (uint32_t)e, r[2 * p + 1] = (uint32_t)(e >> 32);
+        }
+        tmem_st16(tad + c0, r);
+      };
+      for (c0 = 0; c0 + 16 <= lim8; c0 += 16) pass2(c0, std::false_type());
+      for (; c0 < Lp; c0 += 16) pass2(c0, std::true_type());
+      const float te0 = ntail > 0 ? tail_exp_nonpos(tx0) : 0.f;
+      const float te1 = ntail > 1 ? tail_exp_nonpos(tx1) : 0.f;
+      const float te2 = ntail > 2 ? tail_exp_nonpos(tx2) : 0.f;
+      u64 c01 = add2(ch[0], ch[2], c), c23 = add2(ch[1], ch[3], c);
+      if (nfull & 1) c01 = add2(c01, tp01, c), c23 = add2(c23, tp23, c);
+      float s = __fadd_rn(__fadd_rn(lo2(c01), lo2(c23)), __fadd_rn(hi2(c01), hi2(c23)));
+      if (ntail > 0) s = __fadd_rn(s, te0);
+      if (ntail > 1) s = __fadd_rn(s, te1);
+      if (ntail > 2) s = __fadd_rn(s, te2);
+      tmem_wait_st();
+
+      // pass 3: out.col = e / sum (one refined reciprocal per row, IEEE division outside its proven range)
+      const float rg = refined_rcp(s);
+      const u64 R = pk1(rg), NS = pk1(-s);
+      float* qrow = a.Q + (size_t)(valid ? i : 0) * Lp;
+      auto pass3 = [&](int c0, auto edge_t) {
+        constexpr bool EDGE = decltype(edge_t)::value;
+        uint32_t r[16];
+        tmem_ld16(tad + c0, r);
+        tmem_wait_ld();
+        float o[16];
+#pragma unroll
+        for (int p = 0; p < 8; p++) {
+          const int l = c0 + 2 * p;
+          u64 e = pk2(__uint_as_float(r[2 * p]), __uint_as_float(r[2 * p + 1]));
+          if (EDGE) {
+            if (l == lim4) e = pk2(te0, te1);
+            if (l == lim4 + 2) e = pk2(te2, 0.f);
+          }
+          u64 qv;
+          if (small) {
+            qv = pk2(__fdiv_rn(lo2(e), s), __fdiv_rn(hi2(e), s));
+          } else {  // div_shared (softmax_math.cuh) for two
+            const u64 q0 = fma2(e, R, 0ull);
+            const u64 rem = fma2(NS, q0, e);
+            qv = fma2(R, rem, q0);
+          }
+          o[2 * p] = lo2(qv), o[2 * p + 1] = hi2(qv);
+        }
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 4; j++)
+            if (!EDGE || c0 + 4 * j < Lp)
+              *reinterpret_cast<float4*>(qrow + c0 + 4 * j) = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+        }
+      };
+      for (c0 = 0; c0 + 16 <= lim4; c0 += 16) pass3(c0, std::false_type());
+      for (; c0 < Lp; c0 += 16) pass3(c0, std::true_type());
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(b_accempty + 8 * buf);  // the accumulator buffer may be overwritten
+    }
+  }
+
+  __syncthreads();
+  if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encoder() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// fp32 matrix of `rows` rows of `cols` floats (row pitch `pitch` floats) -> boxes of 32 floats x `box_rows` rows, SWIZZLE_128B
+void make_map(CUtensorMap* m, const float* ptr, uint64_t cols, uint64_t rows, uint64_t pitch, uint32_t box_rows) {
+  const cuuint64_t dims[2] = {cols, rows};
+  const cuuint64_t strides[1] = {pitch * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)kKB, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = encoder()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DCRF_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed");
+}
+
+}  // namespace
+
+// shared-memory plan of the TMA kernel: stages of [A][A_lo][B_hi][B_lo], 1024-byte aligned, barriers behind them
+static int tma_stages(int Np, size_t* smem) {
+  const size_t stage = 2 * (size_t)kTM * 128 + 2 * (size_t)Np * 128;
+  const size_t fixed = 1024 /* alignment slack */ + 8 * (3 * kMaxStages + 4) + 16;
+  int S = (int)((227 * 1024 - fixed) / stage);
+  if (S > kMaxStages) S = kMaxStages;
+  *smem = fixed + (size_t)S * stage;
+  return S;
+}
+
+bool update_matrix_tc_tma_supported(RowLayout rl, int nterms) {
+  static const bool on = [] {  // DCRF_B200_TCU_TMA=0: the register-staged kernels of matrix_tc.cu (A/B timing)
+    const char* e = std::getenv("DCRF_B200_TCU_TMA");
+    return !e || std::atoi(e) != 0;
+  }();
+  if (!on || !update_matrix_tc_supported(rl, nterms) || !encoder()) return false;
+  int Np, Kp;
+  matrix_tc_dims(rl, &Np, &Kp);
+  size_t smem;
+  return Kp % kKB == 0 && tma_stages(Np, &smem) >= 2;
+}
+
+void launch_update_matrix_tc_tma(Ctx cx, RowLayout rl, TCUArgs a) {
+  LaunchScope ls(cx.prof, cx.stream, "update_matrix_tc");
+  a.L = rl.L, a.Lp = rl.Lp;
+  matrix_tc_dims(rl, &a.Np, &a.Kp);
+  TmaArgs ta;
+  size_t smem;
+  ta.nstages = tma_stages(a.Np, &smem);
+  ta.c_one = 1.f, ta.c_nzero = -0.f, ta.c_mone = -1.f;
+  TmaMaps maps;
+  for (int k = 0; k < a.nterms; k++) {
+    make_map(&maps.a[k], a.t[k].msg, (uint64_t)a.Lp, (uint64_t)a.N, (uint64_t)a.Lp, kTM);
+    make_map(&maps.bhi[k], a.t[k].Bhi, (uint64_t)a.Kp, (uint64_t)a.Np, (uint64_t)a.Kp, (uint32_t)a.Np);
+    make_map(&maps.blo[k], a.t[k].Blo, (uint64_t)a.Kp, (uint64_t)a.Np, (uint64_t)a.Kp, (uint32_t)a.Np);
+  }
+  for (int k = a.nterms; k < kMaxTCUTerms; k++) maps.a[k] = maps.a[0], maps.bhi[k] = maps.bhi[0], maps.blo[k] = maps.blo[0];
+  ta.a = a;
+  DCRF_CUDA(cudaFuncSetAttribute(k_update_matrix_tc_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int ntiles = (a.N + kTM - 1) / kTM;
+  k_update_matrix_tc_tma<<<std::min(ntiles, sms), kThreads, smem, cx.stream>>>(maps, ta);
+}
+
+}  // namespace dcrf
