@@ -21,6 +21,7 @@
 // The accumulator is double-buffered in TMEM (2 x 256 columns): tile t+1's main loop runs under tile t's epilogue.
 #include <cuda.h>  // CUtensorMap and the encoder's signature only; the entry point comes from cudaGetDriverEntryPoint
 
+#include <cstdio>
 #include <cstdlib>
 #include <type_traits>
 
@@ -32,11 +33,17 @@ namespace dcrf {
 namespace {
 
 constexpr int kTM = 128;        // pixels per tile = UMMA M
-constexpr int kKB = 32;         // floats per K slab: one 128-byte swizzle row
-constexpr int kThreads = 512;   // 16 warps: 0 TMA, 1 MMA, 2 TMEM allocation, 4-7 split, 8-15 epilogue
+#ifndef TCU_KB
+#define TCU_KB 32
+#endif
+constexpr int kKB = TCU_KB;     // floats per K slab = one swizzle row: 32 (SWIZZLE_128B) or 16 (SWIZZLE_64B, twice the stages)
+constexpr int kRB = kKB * 4;    // bytes per operand row in shared memory
+static_assert(kKB == 32 || kKB == 16, "K slab = one 128- or 64-byte swizzle row");
+// warps: 0 TMA, 1 MMA, 2 TMEM allocation, 4-7 split, 8.. epilogue (four per accumulator buffer)
+constexpr int kMaxBufs = 3;
 constexpr int kSplitWarp0 = 4, kSplitThreads = 128;
 constexpr int kEpiWarp0 = 8;
-constexpr int kMaxStages = 4;
+constexpr int kMaxStages = 8;
 
 struct TmaMaps {
   CUtensorMap a[kMaxTCUTerms], bhi[kMaxTCUTerms], blo[kMaxTCUTerms];
@@ -58,6 +65,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
         : "memory");
   }
 }
+// for the roles with slack (epilogue, TMA producer): poll, then sleep, so that their waiting does not take issue slots from
+// the warps on the critical path (ncu: 36 % of all issued instructions were wait-loop iterations without this)
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t mbar, uint32_t parity, uint32_t ns) {
+  for (;;) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t}\n"
+        : "=r"(done)
+        : "r"(mbar), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(ns);
+  }
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t mbar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
 }
@@ -71,10 +94,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(mbar)
       : "memory");
 }
-// shared-memory matrix descriptor, K-major, SWIZZLE_128B: rows of 128 bytes, 8-row groups 1024 bytes apart (SBO),
-// LBO unused for swizzled K-major operands, version 1 (Blackwell), layout type 2 in bits [61,64)
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
-  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+// shared-memory matrix descriptor, K-major, SWIZZLE_128B / SWIZZLE_64B: rows of kRB bytes, 8-row groups 8 * kRB bytes
+// apart (SBO), LBO unused for swizzled K-major operands, version 1 (Blackwell), layout type 2 / 4 in bits [61,64)
+__device__ __forceinline__ uint64_t umma_desc_sw(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)((8 * kRB) >> 4) << 32) | (1ull << 46) |
+         ((kRB == 128 ? 2ull : 4ull) << 61);
 }
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -102,12 +126,20 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// hi = tf32(x), round to nearest with ties away from zero (what cvt.rna.tf32.f32 gives for finite x below 2^127: the
+// messages are finite), as two integer operations instead of the conversion's special-case handling; lo = x - hi is exact
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-  uint32_t h;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
-  hi = __uint_as_float(h);
-  lo = x - hi;  // exact
+  hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+  lo = x - hi;
 }
+
+#ifdef TCU_TIMING  // -DTCU_TIMING: block 0 prints, per role, the clock64 cycles per tile it spent waiting / working
+#define TT_DECL(...) long long __VA_ARGS__
+#define TT_MARK(acc, mark) { const long long n_ = clock64(); acc += n_ - mark; mark = n_; }
+#else
+#define TT_DECL(...)
+#define TT_MARK(acc, mark)
+#endif
 
 struct TmaArgs {
   TCUArgs a;
@@ -115,7 +147,10 @@ struct TmaArgs {
   float c_one, c_nzero, c_mone;  // 1, -0, -1 behind the kernel-argument curtain (packed_math.cuh)
 };
 
-__global__ void __launch_bounds__(kThreads, 1) k_update_matrix_tc_tma(const __grid_constant__ TmaMaps maps, const TmaArgs ta) {
+// NB: accumulator buffers in TMEM = sets of four epilogue warps (3 when 3 * Np <= 512 columns, else 2);
+// W32: rows of U and Q are 32-byte aligned (Lp % 8 == 0) and move in 256-bit pieces
+template <int NB, bool W32>
+__global__ void __launch_bounds__(256 + 128 * NB, 1) k_update_matrix_tc_tma(const __grid_constant__ TmaMaps maps, const TmaArgs ta) {
   extern __shared__ uint8_t smem_raw[];
   const TCUArgs& a = ta.a;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -124,13 +159,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_update_matrix_tc_tma(const __gr
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - raw);
-  const uint32_t szA = kTM * 128, szB = (uint32_t)a.Np * 128;
+  const uint32_t szA = kTM * kRB, szB = (uint32_t)a.Np * kRB;
   const uint32_t stage_bytes = 2 * szA + 2 * szB;  // [A -> A_hi][A_lo][B_hi][B_lo]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + (size_t)S * stage_bytes);
   // bars: full[S] (TMA landed), split[S] (A_hi / A_lo ready), empty[S] (MMAs done reading), accfull[2], accempty[2]
   const uint32_t b_full = smem_u32(bars), b_split = b_full + 8 * kMaxStages, b_empty = b_split + 8 * kMaxStages,
-                 b_accfull = b_empty + 8 * kMaxStages, b_accempty = b_accfull + 16;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kMaxStages + 4);
+                 b_accfull = b_empty + 8 * kMaxStages, b_accempty = b_accfull + 8 * kMaxBufs;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kMaxStages + 2 * kMaxBufs);
 
   if (tid == 0) {
     for (int s = 0; s < S; s++) {
@@ -138,7 +173,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_update_matrix_tc_tma(const __gr
       mbar_init(b_split + 8 * s, kSplitThreads);
       mbar_init(b_empty + 8 * s, 1);
     }
-    for (int b = 0; b < 2; b++) {
+    for (int b = 0; b < NB; b++) {
       mbar_init(b_accfull + 8 * b, 1);
       mbar_init(b_accempty + 8 * b, 4);
     }
@@ -155,16 +190,23 @@ __global__ void __launch_bounds__(kThreads, 1) k_update_matrix_tc_tma(const __gr
   const int ntiles = (a.N + kTM - 1) / kTM;
   const int nslabs = a.Kp / kKB;         // per term
   const int gslabs = nslabs * a.nterms;  // per tile
+  const uint32_t acc_cols = NB == 2 ? 256u : (uint32_t)a.Np;  // TMEM columns between the accumulator buffers
 
   if (warp == 0) {
     // ---------------- TMA producer ---------------------------------------------------------------------------------
     if (lane == 0) {
       int s = 0;
       uint32_t round = 0;
+      TT_DECL(t_wait = 0, t_issue = 0, t_mark = clock64(); int nt = 0);
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         int term = 0, slab = 0;
+#ifdef TCU_TIMING
+        nt++;
+#endif
         for (int g = 0; g < gslabs; g++) {
-          if (round > 0) mbar_wait(b_empty + 8 * s, (round - 1) & 1);
+          TT_MARK(t_issue, t_mark);
+          if (round > 0) mbar_wait_relaxed(b_empty + 8 * s, (round - 1) & 1, 64);
+          TT_MARK(t_wait, t_mark);
           const uint32_t st = base + (uint32_t)s * stage_bytes, fb = b_full + 8 * s;
           mbar_expect_tx(fb, szA + 2 * szB);
           tma_load_2d(st, &maps.a[term], slab * kKB, tile * kTM, fb);
@@ -174,6 +216,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_update_matrix_tc_tma(const __gr
           if (++s == S) s = 0, round++;
         }
       }
+#ifdef TCU_TIMING
+      if (blockIdx.x == 0) printf("[tma] producer, %d tiles: wait empty %lld, issue %lld cycles per tile\n", nt, t_wait / nt, t_issue / nt);
+#endif
     }
   } else if (warp == 1) {
     // ---------------- MMA issue ------------------------------------------------------------------------------------
@@ -182,18 +227,24 @@ __global__ void __launch_bounds__(kThreads, 1) k_update_matrix_tc_tma(const __gr
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.Np >> 3) << 17) | ((uint32_t)(kTM >> 4) << 24);
       int s = 0;
       uint32_t round = 0, tl = 0;
+      TT_DECL(t_acc = 0, t_full = 0, t_split = 0, t_issue = 0, t_mark = clock64());
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tl++) {
-        const uint32_t buf = tl & 1, acc = tmem + buf * 256;
-        if (tl >= 2) mbar_wait(b_accempty + 8 * buf, ((tl >> 1) - 1) & 1);  // drained by the epilogue two tiles ago
+        const uint32_t buf = tl % NB, use = tl / NB, acc = tmem + buf * acc_cols;
+        TT_MARK(t_issue, t_mark);
+        if (use > 0) mbar_wait(b_accempty + 8 * buf, (use - 1) & 1);  // drained by the epilogue of its previous tile
+        TT_MARK(t_acc, t_mark);
         for (int g = 0; g < gslabs; g++) {
+          TT_MARK(t_issue, t_mark);
           mbar_wait(b_full + 8 * s, round & 1);
+          TT_MARK(t_full, t_mark);
           mbar_wait(b_split + 8 * s, round & 1);
+          TT_MARK(t_split, t_mark);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t st = base + (uint32_t)s * stage_bytes;
 #pragma unroll
           for (int ks = 0; ks < kKB / 8; ks++) {  // one k-step = 8 tf32 = 32 bytes inside the 128-byte swizzle row
-            const uint64_t ahi = umma_desc_sw128(st + ks * 32), alo = umma_desc_sw128(st + szA + ks * 32);
-            const uint64_t bhi = umma_desc_sw128(st + 2 * szA + ks * 32), blo = umma_desc_sw128(st + 2 * szA + szB + ks * 32);
+            const uint64_t ahi = umma_desc_sw(st + ks * 32), alo = umma_desc_sw(st + szA + ks * 32);
+            const uint64_t bhi = umma_desc_sw(st + 2 * szA + ks * 32), blo = umma_desc_sw(st + 2 * szA + szB + ks * 32);
             umma_tf32(acc, ahi, bhi, idesc, (g | ks) ? 1u : 0u);
             umma_tf32(acc, alo, bhi, idesc, 1u);
             umma_tf32(acc, ahi, blo, idesc, 1u);
@@ -203,34 +254,50 @@ __global__ void __launch_bounds__(kThreads, 1) k_update_matrix_tc_tma(const __gr
           if (++s == S) s = 0, round++;
         }
       }
+#ifdef TCU_TIMING
+      if (blockIdx.x == 0 && tl) printf("[tma] mma, %u tiles: wait accumulator drained %lld, wait TMA %lld, wait split %lld, issue %lld cycles per tile\n", tl, t_acc / tl, t_full / tl, t_split / tl, t_issue / tl);
+#endif
     }
   } else if (warp >= kSplitWarp0 && warp < kSplitWarp0 + kSplitThreads / 32) {
     // ---------------- message slab -> tf32 hi (in place) + lo ----------------------------------------------------------
     const int t = tid - kSplitWarp0 * 32;
     int s = 0;
     uint32_t round = 0;
+    TT_DECL(t_wait = 0, t_work = 0, t_fence = 0, t_mark = clock64(); int nt = 0);
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+#ifdef TCU_TIMING
+      nt++;
+#endif
       for (int g = 0; g < gslabs; g++) {
+        TT_MARK(t_work, t_mark);
         mbar_wait(b_full + 8 * s, round & 1);
+        TT_MARK(t_wait, t_mark);
         float4* A = reinterpret_cast<float4*>(sm + (size_t)s * stage_bytes);
         float4* Alo = reinterpret_cast<float4*>(sm + (size_t)s * stage_bytes + szA);
+        constexpr int kPer = (int)(kTM * kRB / 16) / kSplitThreads;
+        float4 v[kPer];
 #pragma unroll
-        for (int i = 0; i < (int)(kTM * 128 / 16) / kSplitThreads; i++) {
-          const int e = t + i * kSplitThreads;
-          const float4 v = A[e];
+        for (int i = 0; i < kPer; i++) v[i] = A[t + i * kSplitThreads];
+#pragma unroll
+        for (int i = 0; i < kPer; i++) {
           float4 h, l;
-          split_tf32(v.x, h.x, l.x);
-          split_tf32(v.y, h.y, l.y);
-          split_tf32(v.z, h.z, l.z);
-          split_tf32(v.w, h.w, l.w);
-          A[e] = h;
-          Alo[e] = l;
+          split_tf32(v[i].x, h.x, l.x);
+          split_tf32(v[i].y, h.y, l.y);
+          split_tf32(v[i].z, h.z, l.z);
+          split_tf32(v[i].w, h.w, l.w);
+          A[t + i * kSplitThreads] = h;
+          Alo[t + i * kSplitThreads] = l;
         }
+        TT_MARK(t_work, t_mark);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA's async proxy
         mbar_arrive(b_split + 8 * s);
+        TT_MARK(t_fence, t_mark);
         if (++s == S) s = 0, round++;
       }
     }
+#ifdef TCU_TIMING
+    if (blockIdx.x == 0 && t == 0) printf("[tma] split, %d tiles: wait TMA %lld, work %lld, fence + arrive %lld cycles per tile\n", nt, t_wait / nt, t_work / nt, t_fence / nt);
+#endif
   } else if (warp >= kEpiWarp0) {
     // ---------------- epilogue: one thread per pixel row -----------------------------------------------------------------
     const int set = (warp - kEpiWarp0) >> 2, q = warp & 3;  // a warp may touch the TMEM lanes 32 * (warp % 4) ..
@@ -240,42 +307,63 @@ __global__ void __launch_bounds__(kThreads, 1) k_update_matrix_tc_tma(const __gr
     c.one = pk1(ta.c_one), c.nzero = pk1(ta.c_nzero), c.mone = pk1(ta.c_mone);
     const u64 Z = pk1(a.neg_unary ? -0.f : 0.f);
     uint32_t tl = 0;
+    TT_DECL(t_wait = 0, t_p1 = 0, t_p2 = 0, t_p3 = 0, t_mark = clock64(); int nt = 0);
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tl++) {
-      if ((int)(tl & 1) != set) continue;
-      const uint32_t buf = tl & 1;
-      const uint32_t tad = tmem + buf * 256 + ((uint32_t)(q * 32) << 16);
+      if ((int)(tl % NB) != set) continue;
+#ifdef TCU_TIMING
+      nt++;
+#endif
+      const uint32_t buf = set, use = tl / NB;
+      const uint32_t tad = tmem + buf * acc_cols + ((uint32_t)(q * 32) << 16);
       const int i = tile * kTM + q * 32 + lane;
       const bool valid = i < a.N;
       const float* urow = (a.U && valid) ? a.U + (size_t)i * Lp : nullptr;
-      float4 un[4];
-      auto load_u = [&](int c0) {
+      // 16 unary values as pairs; two register sets that trade places chunk by chunk, so the loads of chunk c+1 are in
+      // flight while chunk c is processed (a copy from a single "next" set would wait for them at once)
+      u64 ua[8], ub[8];
+      auto load_u = [&](int c0, u64 (&un)[8]) {
+        if (W32) {
 #pragma unroll
-        for (int j = 0; j < 4; j++)
-          un[j] = (urow && c0 + 4 * j < Lp) ? __ldg(reinterpret_cast<const float4*>(urow + c0 + 4 * j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int j = 0; j < 2; j++) {
+            const F8 v = (urow && c0 + 8 * j < Lp) ? ld8_nc(urow + c0 + 8 * j) : zero8();
+#pragma unroll
+            for (int k = 0; k < 4; k++) un[4 * j + k] = v.p[k];
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const float4 v = (urow && c0 + 4 * j < Lp) ? __ldg(reinterpret_cast<const float4*>(urow + c0 + 4 * j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            un[2 * j] = pk2(v.x, v.y), un[2 * j + 1] = pk2(v.z, v.w);
+          }
+        }
       };
-      load_u(0);
-      mbar_wait(b_accfull + 8 * buf, (tl >> 1) & 1);
+      load_u(0, ua);
+      // the rest of this tile's unary rows on their way into L2 while the set waits for the accumulator (about one tile
+      // time: prefetching the set's NEXT tile instead, three tile times ahead, was evicted again before use -- ncu showed
+      // the unary read twice from DRAM)
+      if (urow) {
+        const char* nu = reinterpret_cast<const char*>(urow);
+        for (int b = 128; b < Lp * 4; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nu + b));
+      }
+      TT_MARK(t_p3, t_mark);
+      mbar_wait_relaxed(b_accfull + 8 * buf, use & 1, 256);
+      TT_MARK(t_wait, t_mark);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
       // Every pass walks the row in chunks of 16 columns; chunks that lie wholly inside the region a pass treats uniformly
       // take the branch-free body (edge = false), the last one or two the general one.
       // pass 1: x = (-U) - accumulator back into TMEM, row maximum and minimum
       float mx = -INFINITY, mn = INFINITY;
-      auto pass1 = [&](int c0, auto edge_t) {
+      auto pass1 = [&](int c0, u64 (&uc)[8], u64 (&un)[8], auto edge_t) {
         constexpr bool EDGE = decltype(edge_t)::value;
         uint32_t r[16];
         tmem_ld16(tad + c0, r);
-        float4 uc[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) uc[j] = un[j];
-        if (c0 + 16 < Lp) load_u(c0 + 16);
+        if (c0 + 16 < Lp) load_u(c0 + 16, un);
         tmem_wait_ld();
 #pragma unroll
         for (int p = 0; p < 8; p++) {
           const int l = c0 + 2 * p;
-          const float4 u4 = uc[p >> 1];
-          const u64 up = (p & 1) ? pk2(u4.z, u4.w) : pk2(u4.x, u4.y);
-          const u64 x = sub2(sub2(Z, up, c), pk2(__uint_as_float(r[2 * p]), __uint_as_float(r[2 * p + 1])), c);
+          const u64 x = sub2(sub2(Z, uc[p], c), pk2(__uint_as_float(r[2 * p]), __uint_as_float(r[2 * p + 1])), c);
           if (!EDGE || l + 1 < L) {
             mx = fmaxf(mx, fmaxf(lo2(x), hi2(x)));
             mn = fminf(mn, fminf(lo2(x), hi2(x)));
@@ -287,10 +375,19 @@ __global__ void __launch_bounds__(kThreads, 1) k_update_matrix_tc_tma(const __gr
         }
         tmem_st16(tad + c0, r);
       };
+      auto pass1_at = [&](int c0, u64 (&uc)[8], u64 (&un)[8]) {
+        if (c0 + 16 <= L)
+          pass1(c0, uc, un, std::false_type());
+        else
+          pass1(c0, uc, un, std::true_type());
+      };
       int c0 = 0;
-      for (; c0 + 16 <= L; c0 += 16) pass1(c0, std::false_type());
-      for (; c0 < Lp; c0 += 16) pass1(c0, std::true_type());
+      for (; c0 < Lp; c0 += 32) {
+        pass1_at(c0, ua, ub);
+        if (c0 + 16 < Lp) pass1_at(c0 + 16, ub, ua);
+      }
       tmem_wait_st();
+      TT_MARK(t_p1, t_mark);
       // some exp(x - max) of this row is below the range the shared-reciprocal division is proven for (x - max is
       // monotonic in x, so the row minimum decides)
       const bool small = __fsub_rn(mn, mx) < -44.f;
@@ -343,6 +440,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_update_matrix_tc_tma(const __gr
       if (ntail > 1) s = __fadd_rn(s, te1);
       if (ntail > 2) s = __fadd_rn(s, te2);
       tmem_wait_st();
+      TT_MARK(t_p2, t_mark);
 
       // pass 3: out.col = e / sum (one refined reciprocal per row, IEEE division outside its proven range)
       const float rg = refined_rcp(s);
@@ -373,10 +471,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_update_matrix_tc_tma(const __gr
           o[2 * p] = lo2(qv), o[2 * p + 1] = hi2(qv);
         }
         if (valid) {
+          if (W32) {
 #pragma unroll
-          for (int j = 0; j < 4; j++)
-            if (!EDGE || c0 + 4 * j < Lp)
-              *reinterpret_cast<float4*>(qrow + c0 + 4 * j) = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+            for (int j = 0; j < 2; j++)
+              if (!EDGE || c0 + 8 * j < Lp) {
+                F8 v;
+#pragma unroll
+                for (int k = 0; k < 4; k++) v.p[k] = pk2(o[8 * j + 2 * k], o[8 * j + 2 * k + 1]);
+                st8(qrow + c0 + 8 * j, v);
+              }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+              if (!EDGE || c0 + 4 * j < Lp)
+                *reinterpret_cast<float4*>(qrow + c0 + 4 * j) = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+          }
         }
       };
       for (c0 = 0; c0 + 16 <= lim4; c0 += 16) pass3(c0, std::false_type());
@@ -384,7 +493,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_update_matrix_tc_tma(const __gr
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(b_accempty + 8 * buf);  // the accumulator buffer may be overwritten
+      TT_MARK(t_p3, t_mark);
     }
+#ifdef TCU_TIMING
+    if (blockIdx.x == 0 && lane == 0 && q == 0 && nt) printf("[tma] epilogue set %d, %d tiles: wait accumulator %lld, pass 1 %lld, pass 2 %lld, pass 3 %lld cycles per tile\n", set, nt, t_wait / nt, t_p1 / nt, t_p2 / nt, t_p3 / nt);
+#endif
   }
 
   __syncthreads();
@@ -414,7 +527,7 @@ void make_map(CUtensorMap* m, const float* ptr, uint64_t cols, uint64_t rows, ui
   const cuuint32_t box[2] = {(cuuint32_t)kKB, box_rows};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = encoder()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
-                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, kRB == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   DCRF_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed");
 }
@@ -423,8 +536,8 @@ void make_map(CUtensorMap* m, const float* ptr, uint64_t cols, uint64_t rows, ui
 
 // shared-memory plan of the TMA kernel: stages of [A][A_lo][B_hi][B_lo], 1024-byte aligned, barriers behind them
 static int tma_stages(int Np, size_t* smem) {
-  const size_t stage = 2 * (size_t)kTM * 128 + 2 * (size_t)Np * 128;
-  const size_t fixed = 1024 /* alignment slack */ + 8 * (3 * kMaxStages + 4) + 16;
+  const size_t stage = 2 * (size_t)kTM * kRB + 2 * (size_t)Np * kRB;
+  const size_t fixed = 1024 /* alignment slack */ + 8 * (3 * kMaxStages + 2 * kMaxBufs) + 16;
   int S = (int)((227 * 1024 - fixed) / stage);
   if (S > kMaxStages) S = kMaxStages;
   *smem = fixed + (size_t)S * stage;
@@ -432,11 +545,11 @@ static int tma_stages(int Np, size_t* smem) {
 }
 
 bool update_matrix_tc_tma_supported(RowLayout rl, int nterms) {
-  static const bool on = [] {  // DCRF_B200_TCU_TMA=0: the register-staged kernels of matrix_tc.cu (A/B timing)
+  static const bool on = [] {  // DCRF_B200_TCU_TMA=0: no fused tensor-core update; the staged slice -> GEMM -> softmax path (A/B timing)
     const char* e = std::getenv("DCRF_B200_TCU_TMA");
     return !e || std::atoi(e) != 0;
   }();
-  if (!on || !update_matrix_tc_supported(rl, nterms) || !encoder()) return false;
+  if (!on || !matrix_tc_supported(rl) || nterms < 1 || nterms > kMaxTCUTerms || !encoder()) return false;
   int Np, Kp;
   matrix_tc_dims(rl, &Np, &Kp);
   size_t smem;
@@ -459,12 +572,20 @@ void launch_update_matrix_tc_tma(Ctx cx, RowLayout rl, TCUArgs a) {
   }
   for (int k = a.nterms; k < kMaxTCUTerms; k++) maps.a[k] = maps.a[0], maps.bhi[k] = maps.bhi[0], maps.blo[k] = maps.blo[0];
   ta.a = a;
-  DCRF_CUDA(cudaFuncSetAttribute(k_update_matrix_tc_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int ntiles = (a.N + kTM - 1) / kTM;
-  k_update_matrix_tc_tma<<<std::min(ntiles, sms), kThreads, smem, cx.stream>>>(maps, ta);
+  auto go = [&](auto kern, int nb) {
+    DCRF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<std::min(ntiles, sms), 256 + 128 * nb, smem, cx.stream>>>(maps, ta);
+  };
+  const bool w32 = a.Lp % 8 == 0;
+  if (3 * a.Np <= 512) {
+    if (w32) go(k_update_matrix_tc_tma<3, true>, 3); else go(k_update_matrix_tc_tma<3, false>, 3);
+  } else {
+    if (w32) go(k_update_matrix_tc_tma<2, true>, 2); else go(k_update_matrix_tc_tma<2, false>, 2);
+  }
 }
 
 }  // namespace dcrf
