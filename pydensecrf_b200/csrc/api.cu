@@ -1654,11 +1654,10 @@ struct BatchChunk {
     DCRF_CUDA(cudaGetLastError());
     DCRF_CUDA(cudaStreamSynchronize(s));  // the caller's buffers are free again; compute() starts from resident data
   }
-  void compute(int16_t* const* labels, float* const* q_out) {
+  // both lattices and their norm vectors (hash insert, sort, neighbour tables; one host round trip for the vertex count)
+  void build() {
     DeviceGuard g(m->device);
     cudaStream_t s = m->stream;
-    Ctx cx = m->cx();
-    const int L = p.L, Lp = m->rl.Lp;
     FeatureSource src{};
     src.kind = FEAT_GAUSS2D;
     src.W = p.W, src.H = p.H;
@@ -1670,6 +1669,13 @@ struct BatchChunk {
     add_term(m, src, 5, DCRF_COMPAT_POTTS, &p.b_w, 1, DCRF_NORMALIZE_SYMMETRIC);
     dev_free(im, s);
     im = nullptr;
+  }
+  // the mean-field iterations and the label map (+ Q) back into page-locked memory
+  void compute(int16_t* const* labels, float* const* q_out) {
+    DeviceGuard g(m->device);
+    cudaStream_t s = m->stream;
+    Ctx cx = m->cx();
+    const int L = p.L, Lp = m->rl.Lp;
     float* q = dev_alloc<float>(N * Lp, s);
     for (Term* t : m->terms) ensure_val(m, t);
     ensure_scratch_if_staged(m);
@@ -1731,6 +1737,11 @@ size_t chunk_arena_bytes(size_t N, int Lp) { return N * (600 + (size_t)Lp * 4 * 
 // one chunk at a time owns a device's SMs (the kernels of two chunks would only evict each other's L2 lines); uploads
 // and the host-side delivery of other chunks run beside it
 std::mutex& device_lock(int dev) {
+  static std::mutex* locks = new std::mutex[64];
+  return locks[((dev < 0 ? 0 : dev)) & 63];
+}
+
+std::mutex& build_lock(int dev) {
   static std::mutex* locks = new std::mutex[64];
   return locks[((dev < 0 ? 0 : dev)) & 63];
 }
@@ -1815,8 +1826,22 @@ dcrf_status dcrf_batch_map_2d(int W, int H, int L, int device, int B, const floa
             ArenaScope scope(arena.base ? &arena : nullptr);
             BatchChunk ch(bp, dev, b0, Bc);
             ch.upload(unary_LxN, rgb_HxWx3);
-            {
+            // two locks per device: the lattice build of one chunk (latency- and atomics-bound kernels with a host round
+            // trip in the middle) runs beside the iterations of another and fills the gaps its host-side work leaves
+            static const bool split = [] {
+              const char* e = std::getenv("DCRF_B200_BATCH_SPLIT_LOCK");
+              return !e || std::atoi(e) != 0;
+            }();
+            if (split) {
+              {
+                std::lock_guard<std::mutex> own(build_lock(ch.m->device));
+                ch.build();
+              }
               std::lock_guard<std::mutex> own(device_lock(ch.m->device));
+              ch.compute(labels, q_out);
+            } else {
+              std::lock_guard<std::mutex> own(device_lock(ch.m->device));
+              ch.build();
               ch.compute(labels, q_out);
             }
             ch.deliver(labels, q_out);

@@ -303,7 +303,15 @@ def test_matrix_compat_tensor_cores(dcrf, po, L, W, H):
 
 @pytest.mark.parametrize("L,W,H,ntype", [(150, 67, 45, "NORMALIZE_SYMMETRIC"), (64, 50, 40, "NORMALIZE_BEFORE"),
                                           (21, 64, 48, "NORMALIZE_AFTER"), (250, 31, 29, "NO_NORMALIZATION"),
-                                          (150, 129, 3, "NORMALIZE_SYMMETRIC")])
+                                          (150, 129, 3, "NORMALIZE_SYMMETRIC"),
+                                          # the other instantiations of the TMA kernel: rows that are not 32-byte aligned
+                                          # with three (20 labels) and two (100 -> Np 112... / 180) accumulator buffers, one
+                                          # label short of / past a 16-column chunk, L % 4 = 1, 2, 3 tails
+                                          (20, 40, 30, "NORMALIZE_SYMMETRIC"), (100, 33, 31, "NORMALIZE_BEFORE"),
+                                          (180, 30, 20, "NORMALIZE_SYMMETRIC"), (33, 41, 37, "NORMALIZE_AFTER"),
+                                          (47, 30, 30, "NORMALIZE_SYMMETRIC"), (130, 25, 21, "NORMALIZE_SYMMETRIC"),
+                                          # several tiles per CTA: accumulator buffers and operand stages go round many times
+                                          (150, 320, 240, "NORMALIZE_SYMMETRIC")])
 def test_tensor_core_update_all_matrix_terms(dcrf, po, L, W, H, ntype):
     """When every term carries a MatrixCompatibility the whole update is one tcgen05 kernel (slice gathers feed the
     A operand, all terms share the TMEM accumulator, the softmax runs in the epilogue).  Held to the tensor-core
@@ -340,7 +348,13 @@ def test_tensor_core_update_all_matrix_terms(dcrf, po, L, W, H, ntype):
     for _ in range(4):
         d.stepInference(Q, t1, t2)
     assert np.abs(np.array(Q) - Qo).max() <= tol
-    assert abs(d.klDivergence(Q) - o.klDivergence(Qo)) <= KL_RTOL * abs(o.klDivergence(Qo)) + 1e-3
+    if W * H * L > 5_000_000:
+        # the reference sums every pairwise term as ONE float reduction (densecrf.cpp:232); over 10^7 products its own
+        # rounding exceeds KL_RTOL, so the large case is compared in the mode that restates that reduction order
+        d.setKLMode(1)
+    kd, ko = d.klDivergence(Q), o.klDivergence(Qo)
+    print("KL %.6f vs oracle %.6f" % (kd, ko))
+    assert abs(kd - ko) <= KL_RTOL * abs(ko) + 1e-3
 
 
 @pytest.mark.parametrize("L,W,H", [(2, 64, 48), (3, 50, 34), (7, 61, 47), (21, 128, 96), (150, 40, 30), (33, 31, 29)])
