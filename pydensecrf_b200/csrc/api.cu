@@ -1610,6 +1610,12 @@ dcrf_status dcrf_flush_l2(dcrf_t* m) {
 
 namespace {
 
+// end of the iterations of the chunk that last held a device's lock (guarded by that lock)
+cudaEvent_t& last_compute_done(int dev) {
+  static cudaEvent_t* ev = new cudaEvent_t[64]();
+  return ev[((dev < 0 ? 0 : dev)) & 63];
+}
+
 struct BatchParams {
   int W, H, L, n_iterations;
   float g_sx, g_sy, g_w, b_sx, b_sy, b_sr, b_sg, b_sb, b_w;
@@ -1671,11 +1677,16 @@ struct BatchChunk {
     im = nullptr;
   }
   // the mean-field iterations and the label map (+ Q) back into page-locked memory
+  // Enqueue only (call under the device lock): the stream first waits for the event that marks the end of the previous
+  // chunk's iterations on this device, so chunks own the SMs one after the other WITHOUT a host round trip between
+  // them -- the next worker queues its launches while this chunk is still running.  finish() synchronises, outside the lock.
   void compute(int16_t* const* labels, float* const* q_out) {
     DeviceGuard g(m->device);
     cudaStream_t s = m->stream;
     Ctx cx = m->cx();
     const int L = p.L, Lp = m->rl.Lp;
+    cudaEvent_t& prev = last_compute_done(m->device);
+    if (prev) DCRF_CUDA(cudaStreamWaitEvent(s, prev, 0));
     float* q = dev_alloc<float>(N * Lp, s);
     for (Term* t : m->terms) ensure_val(m, t);
     ensure_scratch_if_staged(m);
@@ -1684,6 +1695,13 @@ struct BatchChunk {
     mf_run(m, q, p.n_iterations);
     int16_t* dl = dev_alloc<int16_t>(N, s);
     launch_argmax(cx, m->rl, (int)N, q, dl);
+    {  // the next chunk may start its kernels here (its copies back to the host overlap)
+      cudaEvent_t done;
+      DCRF_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+      DCRF_CUDA(cudaEventRecord(done, s));
+      if (prev) cudaEventDestroy(prev);  // legal while a stream still waits on it: released when it has completed
+      prev = done;
+    }
     int16_t* hl = (int16_t*)g_pinned.get(N * sizeof(int16_t));
     float* hq = nullptr;
     try {
@@ -1698,7 +1716,6 @@ struct BatchChunk {
       dev_free(dl, s);
       dev_free(q, s);
       DCRF_CUDA(cudaGetLastError());
-      DCRF_CUDA(cudaStreamSynchronize(s));
     } catch (...) {
       cudaStreamSynchronize(s);
       g_pinned.put(hl, N * sizeof(int16_t));
@@ -1708,6 +1725,18 @@ struct BatchChunk {
     hl_ = hl, hq_ = hq;
     (void)labels;
     (void)q_out;
+  }
+  // wait for the chunk's kernels and copies (outside the device lock)
+  void finish() {
+    DeviceGuard g(m->device);
+    const cudaError_t e = cudaStreamSynchronize(m->stream);
+    if (e != cudaSuccess) {
+      const int L = p.L;
+      if (hl_) g_pinned.put(hl_, N * sizeof(int16_t));
+      if (hq_) g_pinned.put(hq_, N * L * sizeof(float));
+      hl_ = nullptr, hq_ = nullptr;
+      DCRF_CUDA(e);
+    }
   }
   // host-side scatter of the results into the caller's per-image arrays (outside the device lock)
   void deliver(int16_t* const* labels, float* const* q_out) {
@@ -1837,12 +1866,16 @@ dcrf_status dcrf_batch_map_2d(int W, int H, int L, int device, int B, const floa
                 std::lock_guard<std::mutex> own(build_lock(ch.m->device));
                 ch.build();
               }
-              std::lock_guard<std::mutex> own(device_lock(ch.m->device));
-              ch.compute(labels, q_out);
+              {
+                std::lock_guard<std::mutex> own(device_lock(ch.m->device));
+                ch.compute(labels, q_out);
+              }
+              ch.finish();
             } else {
               std::lock_guard<std::mutex> own(device_lock(ch.m->device));
               ch.build();
               ch.compute(labels, q_out);
+              ch.finish();
             }
             ch.deliver(labels, q_out);
           } catch (const Error& e) {
