@@ -683,6 +683,12 @@ void mf_init(dcrf_model* m, float* Q, bool qn_out = false, bool keep_q = true) {
     a.N = m->N, a.W = m->W, a.H = m->H, a.nterms = 0, a.U = m->U, a.neg_unary = 1, a.Q = Q;
     set_outputs(m, a, qn_out, keep_q);
     run_fused(m, a);
+  } else if (m->iter_mode != 1 && m->U && update_matrix_tc_tma_supported(m->rl, 0)) {
+    // more than 128 labels: the thread-per-row softmax of the tensor-core update kernel without its main loop (one pass
+    // over U and Q instead of the accumulator round trip of the staged form)
+    TCUArgs a;
+    a.N = m->N, a.nterms = 0, a.U = m->U, a.neg_unary = 1, a.Q = Q;
+    launch_update_matrix_tc_tma(cx, m->rl, a);
   } else {
     ensure_scratch(m);
     launch_init_acc(cx, m->rl, m->N, m->U, true, m->acc);

@@ -23,6 +23,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <type_traits>
 
 #include "common.h"
@@ -222,7 +223,7 @@ __global__ void __launch_bounds__(256 + 128 * NB, 1) k_update_matrix_tc_tma(cons
     }
   } else if (warp == 1) {
     // ---------------- MMA issue ------------------------------------------------------------------------------------
-    if (lane == 0) {
+    if (lane == 0 && gslabs > 0) {
       // instruction descriptor: D fp32, A/B tf32, both K-major, N = Np, M = 128
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.Np >> 3) << 17) | ((uint32_t)(kTM >> 4) << 24);
       int s = 0;
@@ -346,7 +347,7 @@ __global__ void __launch_bounds__(256 + 128 * NB, 1) k_update_matrix_tc_tma(cons
         for (int b = 128; b < Lp * 4; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nu + b));
       }
       TT_MARK(t_p3, t_mark);
-      mbar_wait_relaxed(b_accfull + 8 * buf, use & 1, 256);
+      if (gslabs > 0) mbar_wait_relaxed(b_accfull + 8 * buf, use & 1, 256);  // no terms: Q = softmax(-U), the accumulator reads as 0
       TT_MARK(t_wait, t_mark);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
@@ -357,7 +358,12 @@ __global__ void __launch_bounds__(256 + 128 * NB, 1) k_update_matrix_tc_tma(cons
       auto pass1 = [&](int c0, u64 (&uc)[8], u64 (&un)[8], auto edge_t) {
         constexpr bool EDGE = decltype(edge_t)::value;
         uint32_t r[16];
-        tmem_ld16(tad + c0, r);
+        if (gslabs > 0) {
+          tmem_ld16(tad + c0, r);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; j++) r[j] = 0u;
+        }
         if (c0 + 16 < Lp) load_u(c0 + 16, un);
         tmem_wait_ld();
 #pragma unroll
@@ -549,15 +555,16 @@ bool update_matrix_tc_tma_supported(RowLayout rl, int nterms) {
     const char* e = std::getenv("DCRF_B200_TCU_TMA");
     return !e || std::atoi(e) != 0;
   }();
-  if (!on || !matrix_tc_supported(rl) || nterms < 1 || nterms > kMaxTCUTerms || !encoder()) return false;
+  if (!on || !matrix_tc_supported(rl) || nterms < 0 || nterms > kMaxTCUTerms || !encoder()) return false;
   int Np, Kp;
   matrix_tc_dims(rl, &Np, &Kp);
   size_t smem;
   return Kp % kKB == 0 && tma_stages(Np, &smem) >= 2;
 }
 
+// a.nterms == 0: Q = softmax(-U) alone (the start of inference, densecrf.cpp:118-119), the epilogue without a main loop
 void launch_update_matrix_tc_tma(Ctx cx, RowLayout rl, TCUArgs a) {
-  LaunchScope ls(cx.prof, cx.stream, "update_matrix_tc");
+  LaunchScope ls(cx.prof, cx.stream, a.nterms ? "update_matrix_tc" : "init_softmax_rows");
   a.L = rl.L, a.Lp = rl.Lp;
   matrix_tc_dims(rl, &a.Np, &a.Kp);
   TmaArgs ta;
@@ -565,12 +572,12 @@ void launch_update_matrix_tc_tma(Ctx cx, RowLayout rl, TCUArgs a) {
   ta.nstages = tma_stages(a.Np, &smem);
   ta.c_one = 1.f, ta.c_nzero = -0.f, ta.c_mone = -1.f;
   TmaMaps maps;
+  std::memset(&maps, 0, sizeof(maps));
   for (int k = 0; k < a.nterms; k++) {
     make_map(&maps.a[k], a.t[k].msg, (uint64_t)a.Lp, (uint64_t)a.N, (uint64_t)a.Lp, kTM);
     make_map(&maps.bhi[k], a.t[k].Bhi, (uint64_t)a.Kp, (uint64_t)a.Np, (uint64_t)a.Kp, (uint32_t)a.Np);
     make_map(&maps.blo[k], a.t[k].Blo, (uint64_t)a.Kp, (uint64_t)a.Np, (uint64_t)a.Kp, (uint32_t)a.Np);
   }
-  for (int k = a.nterms; k < kMaxTCUTerms; k++) maps.a[k] = maps.a[0], maps.bhi[k] = maps.bhi[0], maps.blo[k] = maps.blo[0];
   ta.a = a;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
