@@ -111,6 +111,39 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a, uint64_t 
 __device__ __forceinline__ void umma_commit(uint32_t mbar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
 }
+// ---- CTA pairs (cta_group::2): the even CTA of a pair issues the MMAs for both, its barriers collect the arrivals of both ----
+constexpr uint32_t kPeerMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared-window address: same offset in the even CTA
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// plain arrive on the even CTA's barrier (what CUTLASS' umma_arrive_2x1SM_sm0 issues).  The data it announces is in the
+// arriving CTA's OWN shared memory / TMEM and has been fenced for the async proxy before; a release at cluster scope here
+// was measured at ~2 k cycles per arrival (profiles/r03i_tma_pair.txt).
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t mbar_cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(mbar_cluster_addr) : "memory");
+}
+// the pair's form of the tile load: executed by both CTAs, each into its own shared memory; the bytes complete on the
+// EVEN CTA's barrier (`mbar` has the rank bit cleared)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t mbar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(mbar), "r"(c0), "r"(c1), "l"(0x1000000000000000ull /* evict normal */)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accumulate) {
+  const uint32_t z = 0;  // no output lanes disabled
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}\n" ::"r"(d_tmem),
+      "l"(a), "l"(b), "r"(idesc), "r"(accumulate), "r"(z)
+      : "memory");
+}
+// arrives (once the MMAs issued so far have completed) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint32_t mbar) {
+  const uint16_t both = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(mbar), "h"(both)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -149,43 +182,59 @@ struct TmaArgs {
 };
 
 // NB: accumulator buffers in TMEM = sets of four epilogue warps (3 when 3 * Np <= 512 columns, else 2);
-// W32: rows of U and Q are 32-byte aligned (Lp % 8 == 0) and move in 256-bit pieces
-template <int NB, bool W32>
+// W32: rows of U and Q are 32-byte aligned (Lp % 8 == 0) and move in 256-bit pieces;
+// PAIR: clusters of two CTAs on one 256-pixel tile pair (tcgen05 cta_group::2, M = 256): each CTA holds its own 128 message
+//       rows and HALF of every W slab (Np / 2 rows); the even CTA's MMA lane issues for both SMs, so an SM reads and stores
+//       half the W operand bytes of the single-CTA form -- the shared-memory pipe is what bounds this kernel.
+template <int NB, bool W32, bool PAIR>
 __global__ void __launch_bounds__(256 + 128 * NB, 1) k_update_matrix_tc_tma(const __grid_constant__ TmaMaps maps, const TmaArgs ta) {
   extern __shared__ uint8_t smem_raw[];
   const TCUArgs& a = ta.a;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int S = ta.nstages;
+  constexpr int TPG = PAIR ? 2 : 1;  // tiles per group (CTA or CTA pair) and step
+  uint32_t rank = 0;
+  if (PAIR) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const int ngroups = (int)gridDim.x / TPG, group = (int)blockIdx.x / TPG;
   // SWIZZLE_128B wants the stage bases on 1024-byte boundaries of the shared window
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - raw);
-  const uint32_t szA = kTM * kRB, szB = (uint32_t)a.Np * kRB;
+  const uint32_t szA = kTM * kRB, szB = (uint32_t)(a.Np / TPG) * kRB;
   const uint32_t stage_bytes = 2 * szA + 2 * szB;  // [A -> A_hi][A_lo][B_hi][B_lo]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + (size_t)S * stage_bytes);
-  // bars: full[S] (TMA landed), split[S] (A_hi / A_lo ready), empty[S] (MMAs done reading), accfull[2], accempty[2]
-  const uint32_t b_full = smem_u32(bars), b_split = b_full + 8 * kMaxStages, b_empty = b_split + 8 * kMaxStages,
-                 b_accfull = b_empty + 8 * kMaxStages, b_accempty = b_accfull + 8 * kMaxBufs;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kMaxStages + 2 * kMaxBufs);
+  // bars: afull[S] (message tile landed; local), bfull[S] (W slabs landed), split[S] (A_hi / A_lo ready), empty[S] (MMAs
+  // done reading; local), accfull[NB] (local), accempty[NB].  In a pair bfull, split and accempty are the EVEN CTA's: its
+  // MMA lane is the only waiter, both CTAs arrive there.
+  const uint32_t b_afull = smem_u32(bars), b_bfull = b_afull + 8 * kMaxStages, b_split = b_bfull + 8 * kMaxStages,
+                 b_empty = b_split + 8 * kMaxStages, b_accfull = b_empty + 8 * kMaxStages, b_accempty = b_accfull + 8 * kMaxBufs;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * kMaxStages + 2 * kMaxBufs);
 
   if (tid == 0) {
     for (int s = 0; s < S; s++) {
-      mbar_init(b_full + 8 * s, 1);
-      mbar_init(b_split + 8 * s, kSplitThreads);
+      mbar_init(b_afull + 8 * s, 1);
+      mbar_init(b_bfull + 8 * s, 1);
+      mbar_init(b_split + 8 * s, TPG);
       mbar_init(b_empty + 8 * s, 1);
     }
     for (int b = 0; b < NB; b++) {
       mbar_init(b_accfull + 8 * b, 1);
-      mbar_init(b_accempty + 8 * b, 4);
+      mbar_init(b_accempty + 8 * b, 4 * TPG);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {  // the same warp of both CTAs
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // the peer's barriers exist before anything arrives on them
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot;
   const int ntiles = (a.N + kTM - 1) / kTM;
@@ -199,7 +248,8 @@ __global__ void __launch_bounds__(256 + 128 * NB, 1) k_update_matrix_tc_tma(cons
       int s = 0;
       uint32_t round = 0;
       TT_DECL(t_wait = 0, t_issue = 0, t_mark = clock64(); int nt = 0);
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int pt = group; pt * TPG < ntiles; pt += ngroups) {
+        const int tile = pt * TPG + (int)rank;  // past the last tile for the odd CTA of the last pair: zero rows
         int term = 0, slab = 0;
 #ifdef TCU_TIMING
         nt++;
@@ -208,11 +258,19 @@ __global__ void __launch_bounds__(256 + 128 * NB, 1) k_update_matrix_tc_tma(cons
           TT_MARK(t_issue, t_mark);
           if (round > 0) mbar_wait_relaxed(b_empty + 8 * s, (round - 1) & 1, 64);
           TT_MARK(t_wait, t_mark);
-          const uint32_t st = base + (uint32_t)s * stage_bytes, fb = b_full + 8 * s;
-          mbar_expect_tx(fb, szA + 2 * szB);
-          tma_load_2d(st, &maps.a[term], slab * kKB, tile * kTM, fb);
-          tma_load_2d(st + 2 * szA, &maps.bhi[term], slab * kKB, 0, fb);
-          tma_load_2d(st + 2 * szA + szB, &maps.blo[term], slab * kKB, 0, fb);
+          const uint32_t st = base + (uint32_t)s * stage_bytes, fa = b_afull + 8 * s, fb = b_bfull + 8 * s;
+          mbar_expect_tx(fa, szA);
+          tma_load_2d(st, &maps.a[term], slab * kKB, tile * kTM, fa);
+          if (PAIR) {  // this CTA's half of the W rows; all four half-slabs of the pair complete on the even CTA's barrier
+            if (rank == 0) mbar_expect_tx(fb, 4 * szB);
+            const int row0 = (int)rank * (a.Np / 2);
+            tma_load_2d_pair(st + 2 * szA, &maps.bhi[term], slab * kKB, row0, fb & kPeerMask);
+            tma_load_2d_pair(st + 2 * szA + szB, &maps.blo[term], slab * kKB, row0, fb & kPeerMask);
+          } else {
+            mbar_expect_tx(fb, 2 * szB);
+            tma_load_2d(st + 2 * szA, &maps.bhi[term], slab * kKB, 0, fb);
+            tma_load_2d(st + 2 * szA + szB, &maps.blo[term], slab * kKB, 0, fb);
+          }
           if (++slab == nslabs) slab = 0, term++;
           if (++s == S) s = 0, round++;
         }
@@ -223,20 +281,22 @@ __global__ void __launch_bounds__(256 + 128 * NB, 1) k_update_matrix_tc_tma(cons
     }
   } else if (warp == 1) {
     // ---------------- MMA issue ------------------------------------------------------------------------------------
-    if (lane == 0 && gslabs > 0) {
-      // instruction descriptor: D fp32, A/B tf32, both K-major, N = Np, M = 128
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.Np >> 3) << 17) | ((uint32_t)(kTM >> 4) << 24);
+    if (lane == 0 && gslabs > 0 && rank == 0) {
+      // instruction descriptor: D fp32, A/B tf32, both K-major, N = Np, M = 128 (256 over the two SMs of a pair)
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.Np >> 3) << 17) | ((uint32_t)((kTM * TPG) >> 4) << 24);
       int s = 0;
       uint32_t round = 0, tl = 0;
       TT_DECL(t_acc = 0, t_full = 0, t_split = 0, t_issue = 0, t_mark = clock64());
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tl++) {
+      for (int pt = group; pt * TPG < ntiles; pt += ngroups, tl++) {
         const uint32_t buf = tl % NB, use = tl / NB, acc = tmem + buf * acc_cols;
         TT_MARK(t_issue, t_mark);
-        if (use > 0) mbar_wait(b_accempty + 8 * buf, (use - 1) & 1);  // drained by the epilogue of its previous tile
+        if (use > 0) {  // drained by the epilogue (of both CTAs) of its previous tile
+          mbar_wait(b_accempty + 8 * buf, (use - 1) & 1);
+        }
         TT_MARK(t_acc, t_mark);
         for (int g = 0; g < gslabs; g++) {
           TT_MARK(t_issue, t_mark);
-          mbar_wait(b_full + 8 * s, round & 1);
+          mbar_wait(b_bfull + 8 * s, round & 1);
           TT_MARK(t_full, t_mark);
           mbar_wait(b_split + 8 * s, round & 1);
           TT_MARK(t_split, t_mark);
@@ -246,12 +306,23 @@ __global__ void __launch_bounds__(256 + 128 * NB, 1) k_update_matrix_tc_tma(cons
           for (int ks = 0; ks < kKB / 8; ks++) {  // one k-step = 8 tf32 = 32 bytes inside the 128-byte swizzle row
             const uint64_t ahi = umma_desc_sw(st + ks * 32), alo = umma_desc_sw(st + szA + ks * 32);
             const uint64_t bhi = umma_desc_sw(st + 2 * szA + ks * 32), blo = umma_desc_sw(st + 2 * szA + szB + ks * 32);
-            umma_tf32(acc, ahi, bhi, idesc, (g | ks) ? 1u : 0u);
-            umma_tf32(acc, alo, bhi, idesc, 1u);
-            umma_tf32(acc, ahi, blo, idesc, 1u);
+            if (PAIR) {
+              umma_tf32_pair(acc, ahi, bhi, idesc, (g | ks) ? 1u : 0u);
+              umma_tf32_pair(acc, alo, bhi, idesc, 1u);
+              umma_tf32_pair(acc, ahi, blo, idesc, 1u);
+            } else {
+              umma_tf32(acc, ahi, bhi, idesc, (g | ks) ? 1u : 0u);
+              umma_tf32(acc, alo, bhi, idesc, 1u);
+              umma_tf32(acc, ahi, blo, idesc, 1u);
+            }
           }
-          umma_commit(b_empty + 8 * s);
-          if (g == gslabs - 1) umma_commit(b_accfull + 8 * buf);
+          if (PAIR) {
+            umma_commit_pair(b_empty + 8 * s);
+            if (g == gslabs - 1) umma_commit_pair(b_accfull + 8 * buf);
+          } else {
+            umma_commit(b_empty + 8 * s);
+            if (g == gslabs - 1) umma_commit(b_accfull + 8 * buf);
+          }
           if (++s == S) s = 0, round++;
         }
       }
@@ -265,13 +336,13 @@ __global__ void __launch_bounds__(256 + 128 * NB, 1) k_update_matrix_tc_tma(cons
     int s = 0;
     uint32_t round = 0;
     TT_DECL(t_wait = 0, t_work = 0, t_fence = 0, t_mark = clock64(); int nt = 0);
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (int pt = group; pt * TPG < ntiles; pt += ngroups) {
 #ifdef TCU_TIMING
       nt++;
 #endif
       for (int g = 0; g < gslabs; g++) {
         TT_MARK(t_work, t_mark);
-        mbar_wait(b_full + 8 * s, round & 1);
+        mbar_wait(b_afull + 8 * s, round & 1);
         TT_MARK(t_wait, t_mark);
         float4* A = reinterpret_cast<float4*>(sm + (size_t)s * stage_bytes);
         float4* Alo = reinterpret_cast<float4*>(sm + (size_t)s * stage_bytes + szA);
@@ -291,7 +362,12 @@ __global__ void __launch_bounds__(256 + 128 * NB, 1) k_update_matrix_tc_tma(cons
         }
         TT_MARK(t_work, t_mark);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA's async proxy
-        mbar_arrive(b_split + 8 * s);
+        // the four split warps meet, ONE thread arrives for the CTA (128 release.cluster arrivals on the peer's barrier
+        // cost 19 k cycles per tile)
+        asm volatile("bar.sync 1, %0;" ::"n"(kSplitThreads) : "memory");
+        if (t == 0) {
+          if (PAIR) mbar_arrive_cluster((b_split + 8 * s) & kPeerMask); else mbar_arrive(b_split + 8 * s);
+        }
         TT_MARK(t_fence, t_mark);
         if (++s == S) s = 0, round++;
       }
@@ -309,8 +385,9 @@ __global__ void __launch_bounds__(256 + 128 * NB, 1) k_update_matrix_tc_tma(cons
     const u64 Z = pk1(a.neg_unary ? -0.f : 0.f);
     uint32_t tl = 0;
     TT_DECL(t_wait = 0, t_p1 = 0, t_p2 = 0, t_p3 = 0, t_mark = clock64(); int nt = 0);
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tl++) {
+    for (int pt = group; pt * TPG < ntiles; pt += ngroups, tl++) {
       if ((int)(tl % NB) != set) continue;
+      const int tile = pt * TPG + (int)rank;
 #ifdef TCU_TIMING
       nt++;
 #endif
@@ -498,7 +575,9 @@ __global__ void __launch_bounds__(256 + 128 * NB, 1) k_update_matrix_tc_tma(cons
       for (; c0 < Lp; c0 += 16) pass3(c0, std::true_type());
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(b_accempty + 8 * buf);  // the accumulator buffer may be overwritten
+      if (lane == 0) {  // the accumulator buffer may be overwritten
+        if (PAIR) mbar_arrive_cluster((b_accempty + 8 * buf) & kPeerMask); else mbar_arrive(b_accempty + 8 * buf);
+      }
       TT_MARK(t_p3, t_mark);
     }
 #ifdef TCU_TIMING
@@ -506,8 +585,15 @@ __global__ void __launch_bounds__(256 + 128 * NB, 1) k_update_matrix_tc_tma(cons
 #endif
   }
 
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+  if (PAIR) cluster_sync_all();  // neither CTA leaves (or frees TMEM) while the other may still touch it
+  if (warp == 2) {
+    if (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+  }
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -541,9 +627,9 @@ void make_map(CUtensorMap* m, const float* ptr, uint64_t cols, uint64_t rows, ui
 }  // namespace
 
 // shared-memory plan of the TMA kernel: stages of [A][A_lo][B_hi][B_lo], 1024-byte aligned, barriers behind them
-static int tma_stages(int Np, size_t* smem) {
-  const size_t stage = 2 * (size_t)kTM * kRB + 2 * (size_t)Np * kRB;
-  const size_t fixed = 1024 /* alignment slack */ + 8 * (3 * kMaxStages + 2 * kMaxBufs) + 16;
+static int tma_stages(int Np, bool pair, size_t* smem) {
+  const size_t stage = 2 * (size_t)kTM * kRB + 2 * (size_t)(pair ? Np / 2 : Np) * kRB;
+  const size_t fixed = 1024 /* alignment slack */ + 8 * (4 * kMaxStages + 2 * kMaxBufs) + 16;
   int S = (int)((227 * 1024 - fixed) / stage);
   if (S > kMaxStages) S = kMaxStages;
   *smem = fixed + (size_t)S * stage;
@@ -559,7 +645,7 @@ bool update_matrix_tc_tma_supported(RowLayout rl, int nterms) {
   int Np, Kp;
   matrix_tc_dims(rl, &Np, &Kp);
   size_t smem;
-  return Kp % kKB == 0 && tma_stages(Np, &smem) >= 2;
+  return Kp % kKB == 0 && tma_stages(Np, false, &smem) >= 2;
 }
 
 // a.nterms == 0: Q = softmax(-U) alone (the start of inference, densecrf.cpp:118-119), the epilogue without a main loop
@@ -567,31 +653,60 @@ void launch_update_matrix_tc_tma(Ctx cx, RowLayout rl, TCUArgs a) {
   LaunchScope ls(cx.prof, cx.stream, a.nterms ? "update_matrix_tc" : "init_softmax_rows");
   a.L = rl.L, a.Lp = rl.Lp;
   matrix_tc_dims(rl, &a.Np, &a.Kp);
-  TmaArgs ta;
-  size_t smem;
-  ta.nstages = tma_stages(a.Np, &smem);
-  ta.c_one = 1.f, ta.c_nzero = -0.f, ta.c_mone = -1.f;
-  TmaMaps maps;
-  std::memset(&maps, 0, sizeof(maps));
-  for (int k = 0; k < a.nterms; k++) {
-    make_map(&maps.a[k], a.t[k].msg, (uint64_t)a.Lp, (uint64_t)a.N, (uint64_t)a.Lp, kTM);
-    make_map(&maps.bhi[k], a.t[k].Bhi, (uint64_t)a.Kp, (uint64_t)a.Np, (uint64_t)a.Kp, (uint32_t)a.Np);
-    make_map(&maps.blo[k], a.t[k].Blo, (uint64_t)a.Kp, (uint64_t)a.Np, (uint64_t)a.Kp, (uint32_t)a.Np);
-  }
-  ta.a = a;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int ntiles = (a.N + kTM - 1) / kTM;
+  // CTA pairs (cta_group::2) when there is a main loop and more than one tile: DCRF_B200_TCU_PAIR=0 for the single-CTA form
+  static const bool pair_on = [] {
+    const char* e = std::getenv("DCRF_B200_TCU_PAIR");
+    return !e || std::atoi(e) != 0;
+  }();
+  const bool pair = pair_on && a.nterms > 0 && ntiles >= 2 && sms >= 2;
+  TmaArgs ta;
+  size_t smem;
+  ta.nstages = tma_stages(a.Np, pair, &smem);
+  ta.c_one = 1.f, ta.c_nzero = -0.f, ta.c_mone = -1.f;
+  TmaMaps maps;
+  std::memset(&maps, 0, sizeof(maps));
+  const uint32_t brows = (uint32_t)(pair ? a.Np / 2 : a.Np);  // W rows per CTA and slab
+  for (int k = 0; k < a.nterms; k++) {
+    make_map(&maps.a[k], a.t[k].msg, (uint64_t)a.Lp, (uint64_t)a.N, (uint64_t)a.Lp, kTM);
+    make_map(&maps.bhi[k], a.t[k].Bhi, (uint64_t)a.Kp, (uint64_t)a.Np, (uint64_t)a.Kp, brows);
+    make_map(&maps.blo[k], a.t[k].Blo, (uint64_t)a.Kp, (uint64_t)a.Np, (uint64_t)a.Kp, brows);
+  }
+  ta.a = a;
   auto go = [&](auto kern, int nb) {
     DCRF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<std::min(ntiles, sms), 256 + 128 * nb, smem, cx.stream>>>(maps, ta);
+    cudaLaunchConfig_t cfg{};
+    cfg.blockDim = dim3(256 + 128 * nb);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = cx.stream;
+    cudaLaunchAttribute attr[1];
+    if (pair) {
+      cfg.gridDim = dim3(2 * std::min((ntiles + 1) / 2, sms / 2));
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr, cfg.numAttrs = 1;
+    } else {
+      cfg.gridDim = dim3(std::min(ntiles, sms));
+    }
+    DCRF_CUDA(cudaLaunchKernelEx(&cfg, kern, maps, ta));
   };
   const bool w32 = a.Lp % 8 == 0;
-  if (3 * a.Np <= 512) {
-    if (w32) go(k_update_matrix_tc_tma<3, true>, 3); else go(k_update_matrix_tc_tma<3, false>, 3);
+  const int nb = 3 * a.Np <= 512 ? 3 : 2;
+  if (pair) {
+    if (nb == 3) {
+      if (w32) go(k_update_matrix_tc_tma<3, true, true>, 3); else go(k_update_matrix_tc_tma<3, false, true>, 3);
+    } else {
+      if (w32) go(k_update_matrix_tc_tma<2, true, true>, 2); else go(k_update_matrix_tc_tma<2, false, true>, 2);
+    }
   } else {
-    if (w32) go(k_update_matrix_tc_tma<2, true>, 2); else go(k_update_matrix_tc_tma<2, false>, 2);
+    if (nb == 3) {
+      if (w32) go(k_update_matrix_tc_tma<3, true, false>, 3); else go(k_update_matrix_tc_tma<3, false, false>, 3);
+    } else {
+      if (w32) go(k_update_matrix_tc_tma<2, true, false>, 2); else go(k_update_matrix_tc_tma<2, false, false>, 2);
+    }
   }
 }
 
