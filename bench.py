@@ -200,6 +200,9 @@ def kernel_bytes(name, lat):
     return float(np.mean(v)) if v else None
 
 
+GRAPH_PRIMING_CALLS = 4  # untimed set-up calls per (model, result matrix) before the warm-up steps, see main()
+
+
 def kernel_sources_sha():
     """sha256 (16 hex digits) over the CUDA sources of the iteration kernels: ties an ncu capture to a build."""
     import hashlib
@@ -294,6 +297,11 @@ def run_b200(args):
     lat = [d._lattice_info(k)[::2] for k in range(2)]  # (d, V)
     Q = eigen.MatrixXf()
 
+    # The engine replays inference(n) as a CUDA graph from the FOURTH identical call on (capture + instantiation cost a few
+    # ms, which one-shot models must not pay): prime it during set-up, so that neither the warm-up steps nor the timed
+    # ones contain the one-off capture (CUDA events on the stream would count the host's capture time as a GPU gap).
+    for _ in range(GRAPH_PRIMING_CALLS):
+        d.inferenceInto(N_ITER, Q)
     for _ in range(max(args.warmup, 3)):
         d.inferenceInto(N_ITER, Q)
     d.synchronize()
@@ -334,7 +342,8 @@ def run_b200(args):
         # warm-up with the timed loop's exact pattern: the previous result stays alive while the next one is computed,
         # so two result matrices (device buffer, page-locked host mirror, CUDA graph each) exist before the clock starts
         out_h = None
-        for _ in range(max(args.warmup, 3) + 1):
+        # (two result matrices alternate, each is replayed as a graph from its fourth use: 2 x GRAPH_PRIMING_CALLS first)
+        for _ in range(2 * GRAPH_PRIMING_CALLS + max(args.warmup, 3) + 1):
             d.setUnaryEnergy(Uh)
             out_h = fetch(d.inference(N_ITER))
         barrier(dist, torch)
@@ -395,7 +404,7 @@ def run_b200(args):
         def pipe_worker(k):
             m, uh = models[k], inputs[k]
             q = Qd = None
-            for _ in range(4):                 # same pattern as the timed loop (two result matrices alive per model)
+            for _ in range(2 * GRAPH_PRIMING_CALLS + 2):   # same pattern as the timed loop (two result matrices alive per model, both replayed as graphs)
                 m.setUnaryEnergy(uh)
                 Qd = m.inference(N_ITER)
                 m.synchronize()
@@ -476,6 +485,8 @@ def run_b200(args):
            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": dict(CONFIG),
            "run_info": {"replicas": world, "cpu_affinity": affinity,
+                        "graph_priming": "%d untimed inference calls per result matrix during set-up, before the warm-up steps: the "
+                                         "engine captures inference(n) as a CUDA graph at the 4th identical call" % GRAPH_PRIMING_CALLS,
                         "lattice_vertices": {"gaussian": lat[0][1], "bilateral": lat[1][1]},
                         "init_ms": {"set_unary": (t1 - t0) * 1e3, "gaussian_lattice": (t2 - t1) * 1e3,
                                     "bilateral_lattice": (t3 - t2) * 1e3}},
