@@ -21,6 +21,7 @@
 // The accumulator is double-buffered in TMEM (2 x 256 columns): tile t+1's main loop runs under tile t's epilogue.
 #include <cuda.h>  // CUtensorMap and the encoder's signature only; the entry point comes from cudaGetDriverEntryPoint
 
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -662,51 +663,64 @@ void launch_update_matrix_tc_tma(Ctx cx, RowLayout rl, TCUArgs a) {
     const char* e = std::getenv("DCRF_B200_TCU_PAIR");
     return !e || std::atoi(e) != 0;
   }();
-  const bool pair = pair_on && a.nterms > 0 && ntiles >= 2 && sms >= 2;
-  TmaArgs ta;
-  size_t smem;
-  ta.nstages = tma_stages(a.Np, pair, &smem);
-  ta.c_one = 1.f, ta.c_nzero = -0.f, ta.c_mone = -1.f;
-  TmaMaps maps;
-  std::memset(&maps, 0, sizeof(maps));
-  const uint32_t brows = (uint32_t)(pair ? a.Np / 2 : a.Np);  // W rows per CTA and slab
-  for (int k = 0; k < a.nterms; k++) {
-    make_map(&maps.a[k], a.t[k].msg, (uint64_t)a.Lp, (uint64_t)a.N, (uint64_t)a.Lp, kTM);
-    make_map(&maps.bhi[k], a.t[k].Bhi, (uint64_t)a.Kp, (uint64_t)a.Np, (uint64_t)a.Kp, brows);
-    make_map(&maps.blo[k], a.t[k].Blo, (uint64_t)a.Kp, (uint64_t)a.Np, (uint64_t)a.Kp, brows);
-  }
-  ta.a = a;
-  auto go = [&](auto kern, int nb) {
-    DCRF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cudaLaunchConfig_t cfg{};
-    cfg.blockDim = dim3(256 + 128 * nb);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = cx.stream;
-    cudaLaunchAttribute attr[1];
+  static std::atomic<bool> pair_ok{true};  // cleared when the device cannot run the two-CTA clusters
+  bool pair = pair_on && pair_ok && a.nterms > 0 && ntiles >= 2 && sms >= 2;
+  for (;;) {
+    TmaArgs ta;
+    size_t smem;
+    ta.nstages = tma_stages(a.Np, pair, &smem);
+    ta.c_one = 1.f, ta.c_nzero = -0.f, ta.c_mone = -1.f;
+    TmaMaps maps;
+    std::memset(&maps, 0, sizeof(maps));
+    const uint32_t brows = (uint32_t)(pair ? a.Np / 2 : a.Np);  // W rows per CTA and slab
+    for (int k = 0; k < a.nterms; k++) {
+      make_map(&maps.a[k], a.t[k].msg, (uint64_t)a.Lp, (uint64_t)a.N, (uint64_t)a.Lp, kTM);
+      make_map(&maps.bhi[k], a.t[k].Bhi, (uint64_t)a.Kp, (uint64_t)a.Np, (uint64_t)a.Kp, brows);
+      make_map(&maps.blo[k], a.t[k].Blo, (uint64_t)a.Kp, (uint64_t)a.Np, (uint64_t)a.Kp, brows);
+    }
+    ta.a = a;
+    auto go = [&](auto kern, int nb) {
+      DCRF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      cudaLaunchConfig_t cfg{};
+      cfg.blockDim = dim3(256 + 128 * nb);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = cx.stream;
+      cudaLaunchAttribute attr[1];
+      if (pair) {
+        cfg.gridDim = dim3(2 * std::min((ntiles + 1) / 2, sms / 2));
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr, cfg.numAttrs = 1;
+        int clusters = 0;  // a device (partition) that cannot co-schedule two such CTAs reports 0: the caller falls back
+        if (cudaOccupancyMaxActiveClusters(&clusters, kern, &cfg) != cudaSuccess || clusters < 1) {
+          cudaGetLastError();
+          return false;
+        }
+      } else {
+        cfg.gridDim = dim3(std::min(ntiles, sms));
+      }
+      DCRF_CUDA(cudaLaunchKernelEx(&cfg, kern, maps, ta));
+      return true;
+    };
+    const bool w32 = a.Lp % 8 == 0;
+    const int nb = 3 * a.Np <= 512 ? 3 : 2;
     if (pair) {
-      cfg.gridDim = dim3(2 * std::min((ntiles + 1) / 2, sms / 2));
-      attr[0].id = cudaLaunchAttributeClusterDimension;
-      attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
-      cfg.attrs = attr, cfg.numAttrs = 1;
+      bool ok;
+      if (nb == 3)
+        ok = w32 ? go(k_update_matrix_tc_tma<3, true, true>, 3) : go(k_update_matrix_tc_tma<3, false, true>, 3);
+      else
+        ok = w32 ? go(k_update_matrix_tc_tma<2, true, true>, 2) : go(k_update_matrix_tc_tma<2, false, true>, 2);
+      if (ok) return;
+      pair_ok = false, pair = false;  // once more in the single-CTA form
+      continue;
     } else {
-      cfg.gridDim = dim3(std::min(ntiles, sms));
+      if (nb == 3) {
+        if (w32) go(k_update_matrix_tc_tma<3, true, false>, 3); else go(k_update_matrix_tc_tma<3, false, false>, 3);
+      } else {
+        if (w32) go(k_update_matrix_tc_tma<2, true, false>, 2); else go(k_update_matrix_tc_tma<2, false, false>, 2);
+      }
     }
-    DCRF_CUDA(cudaLaunchKernelEx(&cfg, kern, maps, ta));
-  };
-  const bool w32 = a.Lp % 8 == 0;
-  const int nb = 3 * a.Np <= 512 ? 3 : 2;
-  if (pair) {
-    if (nb == 3) {
-      if (w32) go(k_update_matrix_tc_tma<3, true, true>, 3); else go(k_update_matrix_tc_tma<3, false, true>, 3);
-    } else {
-      if (w32) go(k_update_matrix_tc_tma<2, true, true>, 2); else go(k_update_matrix_tc_tma<2, false, true>, 2);
-    }
-  } else {
-    if (nb == 3) {
-      if (w32) go(k_update_matrix_tc_tma<3, true, false>, 3); else go(k_update_matrix_tc_tma<3, false, false>, 3);
-    } else {
-      if (w32) go(k_update_matrix_tc_tma<2, true, false>, 2); else go(k_update_matrix_tc_tma<2, false, false>, 2);
-    }
+    return;
   }
 }
 
