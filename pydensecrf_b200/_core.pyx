@@ -84,6 +84,7 @@ cdef extern from "dcrf_b200.h" nogil:
     void dcrf_empty_cache()
     int dcrf_set_matrix_mode(dcrf_t* m, int mode)
     int dcrf_host_alloc(size_t nbytes, void** out)
+    int dcrf_host_alloc_result(size_t nbytes, void** out)
     void dcrf_host_free(void* p, size_t nbytes)
 
 
@@ -130,10 +131,13 @@ cdef class _PinnedBlock:
     cdef Py_ssize_t shape[1]
     cdef Py_ssize_t strides[1]
 
-    def __cinit__(self, size_t nbytes):
+    def __cinit__(self, size_t nbytes, bint result=False):
         self.p = NULL
         self.n = nbytes
-        _check(dcrf_host_alloc(nbytes, &self.p))
+        if result:   # may leave p NULL: too many results of this size are alive, the caller takes ordinary memory
+            _check(dcrf_host_alloc_result(nbytes, &self.p))
+        else:
+            _check(dcrf_host_alloc(nbytes, &self.p))
         self.shape[0] = nbytes
         self.strides[0] = 1
 
@@ -167,6 +171,18 @@ def pinned_empty(shape, dtype="float32"):
     n = int(np.prod(shape)) * dt.itemsize
     blk = _PinnedBlock(max(n, 1))
     return np.frombuffer(blk, dtype=dt, count=int(np.prod(shape))).reshape(shape)
+
+
+def _result_empty(shape, dtype):
+    """Array for a result the caller may keep (label maps): page-locked from the pool while few of its size are alive,
+    ordinary numpy memory otherwise -- pinning a fresh block per call costs more than the copy it speeds up."""
+    import numpy as np
+    dt = np.dtype(dtype)
+    cdef Py_ssize_t cnt = int(np.prod(shape))
+    cdef _PinnedBlock blk = _PinnedBlock(max(cnt * dt.itemsize, 1), True)
+    if blk.p == NULL:
+        return np.empty(shape, dt)
+    return np.frombuffer(blk, dtype=dt, count=cnt).reshape(shape)
 
 
 def abi_version():
@@ -307,7 +323,7 @@ cdef class MatrixXf:
         if self.h == NULL or self.shape[1] == 0:
             return None
         # page-locked (pooled) result memory: the label map arrives by DMA at PCIe rate
-        out = pinned_empty((self.shape[1],), np.int64 if wide else np.int16)
+        out = _result_empty((self.shape[1],), np.int64 if wide else np.int16)
         cdef size_t addr = out.ctypes.data
         cdef dcrf_mat_t* h = self.h
         cdef int st, nb = 8 if wide else 2
@@ -721,7 +737,7 @@ cdef class DenseCRF:
         """Per-variable argmax of Q computed on the device (DenseCRF::currentMap, densecrf.cpp:202-211):
         int16 array of length nvar; only 2 bytes per variable cross PCIe instead of the 4*nlabels of Q."""
         import numpy as np
-        out = pinned_empty((self._nvar,), np.int16)
+        out = _result_empty((self._nvar,), np.int16)
         cdef int16_t[::1] o = out
         cdef dcrf_mat_t* q = Q.handle()
         cdef int st
@@ -734,7 +750,7 @@ cdef class DenseCRF:
         """DenseCRF::map (densecrf.cpp:132-137): inference(n_iterations) followed by currentMap; Q never leaves the GPU.
         int16 array of length nvar."""
         import numpy as np
-        out = pinned_empty((self._nvar,), np.int16)
+        out = _result_empty((self._nvar,), np.int16)
         cdef int16_t[::1] o = out
         cdef int st
         with nogil:
