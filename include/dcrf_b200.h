@@ -185,7 +185,7 @@ dcrf_status dcrf_host_alloc(size_t bytes, void** out);
 void dcrf_empty_cache(void);
 void dcrf_host_free(void* p, size_t bytes);
 /* Page-locked memory for a RESULT (label map, copy of Q) the caller may keep: a pooled block when one is free or fewer than
- * three blocks of this size are out, else *out = NULL and the caller uses ordinary memory (pinning costs ~0.5 ms per MB; a
+ * eight blocks of this size are out, else *out = NULL and the caller uses ordinary memory (pinning costs ~0.5 ms per MB; a
  * caller who keeps every result would pay it per call).  Released with dcrf_host_free. */
 dcrf_status dcrf_host_alloc_result(size_t bytes, void** out);
 

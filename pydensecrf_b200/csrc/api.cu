@@ -100,10 +100,10 @@ struct PinnedPool {
   size_t cached = 0;
   static constexpr size_t kMaxCached = 8ull << 30;
   // Result buffers (the host mirror of a result matrix, a label map): page-locked while at most `max_live` blocks of this
-  // size are out, else nullptr and the caller takes ordinary memory.  Pinning costs ~0.5 ms per MB (82 ms for a 1080p Q),
+  // size are out (eight: several models with two alternating results each stay page-locked), else nullptr and the caller takes ordinary memory.  Pinning costs ~0.5 ms per MB (82 ms for a 1080p Q),
   // which a loop that drops or alternates its results earns back through the pool -- a caller who KEEPS every result
   // (a list of label maps) would pay it on every call (measured: np.argmax 8.5 instead of 0.6 ms at 1080p).
-  void* get_result(size_t bytes, int max_live = 3) {
+  void* get_result(size_t bytes, int max_live = 8) {
     {
       std::lock_guard<std::mutex> g(mu);
       auto it = free_blocks.find(bytes);

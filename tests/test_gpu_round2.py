@@ -242,7 +242,7 @@ def test_pairwise_apply_transpose(dcrf, oracle_built, nt, L):
 
 def test_results_kept_alive_fall_back_to_ordinary_memory(dcrf):
     """Result buffers are page-locked only while few of their size are alive (pinning a fresh block per call costs more
-    than it saves): a caller who keeps every label map / every copy of Q gets ordinary memory from the fourth on -- with
+    than it saves): a caller who keeps every label map / every copy of Q gets ordinary memory from the ninth on -- with
     the same contents."""
     from tests import workloads as wl
 
@@ -252,11 +252,11 @@ def test_results_kept_alive_fall_back_to_ordinary_memory(dcrf):
     d.addPairwiseGaussian(3, 3.0)
     d.addPairwiseBilateral(30, 13, wl.smooth_image(H, W, seed=3, grid=8), 5.0)
     maps, maps16, qs = [], [], []
-    for _ in range(7):
+    for _ in range(12):
         Q = d.inference(3)
         maps.append(np.argmax(Q, axis=0))      # int64 label maps through the NumPy dispatch
         maps16.append(d.currentMap(Q))         # int16 label maps
-        qs.append(np.asarray(Q))               # host views of seven result matrices, all alive
+        qs.append(np.asarray(Q))               # host views of twelve result matrices, all alive
     for m, m16, q in zip(maps[1:], maps16[1:], qs[1:]):
         assert m.dtype == np.int64 and np.array_equal(m, maps[0])
         assert m16.dtype == np.int16 and np.array_equal(m16, maps16[0])
