@@ -93,6 +93,16 @@ void Profiler::destroy() {
 }
 
 // ---- pinned host memory pool: result matrices are re-used across inference calls ----------------
+// Pooled blocks come in size classes (eighths of a power of two, at least 4 KB; <= 12.5 % slack), so that a loop over images
+// of DIFFERENT sizes -- a dataset -- recycles its result buffers like a loop over one size does (measured on 60 different
+// sizes around 500 x 375: 4.8 ms per image with exact-size pools, every image a pool miss, against 2.4 ms for one size).
+static size_t size_class(size_t n) {
+  if (n <= 4096) return 4096;
+  int k = 63 - __builtin_clzll((unsigned long long)n);
+  const size_t step = (size_t)1 << (k - 3);
+  return (n + step - 1) / step * step;
+}
+
 struct PinnedPool {
   std::mutex mu;
   std::multimap<size_t, void*> free_blocks;
@@ -104,6 +114,7 @@ struct PinnedPool {
   // which a loop that drops or alternates its results earns back through the pool -- a caller who KEEPS every result
   // (a list of label maps) would pay it on every call (measured: np.argmax 8.5 instead of 0.6 ms at 1080p).
   void* get_result(size_t bytes, int max_live = 8) {
+    bytes = size_class(bytes);
     {
       std::lock_guard<std::mutex> g(mu);
       auto it = free_blocks.find(bytes);
@@ -119,6 +130,7 @@ struct PinnedPool {
     return get(bytes);
   }
   void* get(size_t bytes) {
+    bytes = size_class(bytes);
     {
       std::lock_guard<std::mutex> g(mu);
       live[bytes]++;
@@ -141,6 +153,7 @@ struct PinnedPool {
     return p;
   }
   void put(void* p, size_t bytes) {
+    bytes = size_class(bytes);
     std::lock_guard<std::mutex> g(mu);
     live[bytes]--;
     if (cached + bytes > kMaxCached) {
@@ -167,6 +180,7 @@ struct DevicePool {
   size_t cached = 0;
   static constexpr size_t kMaxCached = 48ull << 30;
   void* get(int device, size_t bytes) {
+    bytes = size_class(bytes);
     {
       std::lock_guard<std::mutex> g(mu);
       auto it = free_blocks.find({device, bytes});
@@ -192,6 +206,7 @@ struct DevicePool {
     return p;
   }
   void put(int device, void* p, size_t bytes) {
+    bytes = size_class(bytes);
     std::lock_guard<std::mutex> g(mu);
     if (cached + bytes > kMaxCached) {
       cudaFree(p);
