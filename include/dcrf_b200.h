@@ -238,6 +238,35 @@ dcrf_status dcrf_pairwise_apply_transpose(dcrf_t* m, int k, dcrf_mat_t* Q, dcrf_
  * variable i, for pixel-major a, b (N rows of L floats, the layout of MatrixXf::data()); df: N rows of d floats.
  * DenseKernel::kernelGradient (pairwise.cpp:82-86) is exactly this call. */
 dcrf_status dcrf_lattice_gradient(dcrf_t* m, int k, const float* a_NxL, const float* b_NxL, int L, float* df_Nxd);
+/* DenseCRF::gradient (densecrf.cpp:237-297, declared densecrf.h:106): runs n_iterations of mean field keeping every Q,
+ * evaluates the objective on the last one and back-propagates through the iterations.  Any gradient pointer may be NULL
+ * (that gradient is not computed); each receives as many floats as dcrf_num_parameters reports for its group, in the
+ * reference's packing.  *value receives ObjectiveFunction::evaluate's return value.  Sums over the variables are taken in
+ * double in a fixed order (deterministic); against the reference's float Eigen reductions the gradients agree to ~1e-4
+ * relative (tests/test_gpu_gradient.py states the tolerances). */
+typedef enum { DCRF_OBJECTIVE_LOGLIKELIHOOD = 0, DCRF_OBJECTIVE_HAMMING = 1, DCRF_OBJECTIVE_IOU = 2 } dcrf_objective_kind;
+typedef struct {
+  int kind;                  /* dcrf_objective_kind: LogLikelihood / Hamming / IntersectionOverUnion (objective.h:38-74) */
+  const int16_t* gt;         /* ground truth, one label per variable (VectorXs); labels outside [0, nlabels) are ignored */
+  float robust;              /* LogLikelihood(gt, robust) (objective.cpp:35) */
+  const float* class_weight; /* Hamming(gt, w) (objective.cpp:65): n_class_weight floats, must cover every label in gt */
+  int n_class_weight;
+} dcrf_objective;
+dcrf_status dcrf_gradient(dcrf_t* m, int n_iterations, const dcrf_objective* objective, double* value, float* unary_grad,
+                          float* lbl_cmp_grad, float* kernel_grad);
+/* The three parameter vectors of a model (densecrf.h:109-124; densecrf.cpp:298-375):
+ *   DCRF_PARAMS_UNARY               unaryParameters / setUnaryParameters: the logistic unary's L matrix, column-major
+ *                                   (unary.cpp:53-64); empty for a constant unary
+ *   DCRF_PARAMS_LABEL_COMPATIBILITY labelCompatibilityParameters / set...: per term Potts [w], Diagonal w[L], Matrix the
+ *                                   upper triangle row by row (labelcompatibility.cpp:49-99), concatenated over the terms
+ *   DCRF_PARAMS_KERNEL              kernelParameters / set...: per term nothing (CONST_KERNEL), the d feature scales
+ *                                   (DIAG_KERNEL) or the d x d feature transform, column-major (FULL_KERNEL)
+ *                                   (pairwise.cpp:129-151); setting them rebuilds the term's lattice from the transformed
+ *                                   features, as DenseKernel::setParameters does */
+typedef enum { DCRF_PARAMS_UNARY = 0, DCRF_PARAMS_LABEL_COMPATIBILITY = 1, DCRF_PARAMS_KERNEL = 2 } dcrf_param_group;
+dcrf_status dcrf_num_parameters(dcrf_t* m, int group, int* n);
+dcrf_status dcrf_get_parameters(dcrf_t* m, int group, float* out);
+dcrf_status dcrf_set_parameters(dcrf_t* m, int group, const float* v, int n);
 /* 0 = pick automatically, 1 = force the staged (unfused) iteration, 2 = force the fused iteration (fails if
  * the model has a term the fused kernel cannot take) */
 dcrf_status dcrf_set_iteration_mode(dcrf_t* m, int mode);

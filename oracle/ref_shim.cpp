@@ -18,6 +18,7 @@
 #include "pairwise.h"
 #include "labelcompatibility.h"
 #include "unary.h"
+#include "objective.h"
 
 void expAndNormalize(MatrixXf& out, const MatrixXf& in);  // densecrf.cpp:98 (non-static free function)
 
@@ -197,6 +198,52 @@ void ref_pairwise_apply(const float* feat_dxN, int d, int N, int L, int compat_k
   MatrixXf Q = Eigen::Map<const MatrixXf>(Q_NxL, L, N), out;
   pp.apply(out, Q);
   std::memcpy(out_NxL, out.data(), sizeof(float) * (size_t)L * N);
+}
+// ---- learning path: the reference's own DenseCRF::gradient and parameter vectors (densecrf.h:106-124) ----------------
+// group: 0 unary, 1 label compatibility, 2 kernel
+static VectorXf ref_params(Model* m, int group) {
+  return group == 0 ? m->crf->unaryParameters() : group == 1 ? m->crf->labelCompatibilityParameters() : m->crf->kernelParameters();
+}
+int ref_crf_num_params(void* h, int group) { return (int)ref_params(static_cast<Model*>(h), group).rows(); }
+void ref_crf_get_params(void* h, int group, float* out) {
+  VectorXf v = ref_params(static_cast<Model*>(h), group);
+  if (v.rows()) std::memcpy(out, v.data(), sizeof(float) * v.rows());
+}
+void ref_crf_set_params(void* h, int group, const float* v, int n) {
+  Model* m = static_cast<Model*>(h);
+  VectorXf p = Eigen::Map<const VectorXf>(v, n);
+  if (group == 0) m->crf->setUnaryParameters(p);
+  else if (group == 1) m->crf->setLabelCompatibilityParameters(p);
+  else m->crf->setKernelParameters(p);
+}
+// obj_kind: 0 LogLikelihood(gt, robust), 1 Hamming(gt, weights), 2 IntersectionOverUnion(gt); a null gradient pointer
+// skips that gradient, as a null VectorXf* does in the reference
+double ref_crf_gradient(void* h, int n_iter, int obj_kind, const short* gt, float robust, const float* cw, int ncw,
+                        float* unary_grad, float* lbl_cmp_grad, float* kernel_grad) {
+  Model* m = static_cast<Model*>(h);
+  VectorXs g = Eigen::Map<const VectorXs>(gt, m->N);
+  ObjectiveFunction* obj;
+  if (obj_kind == 0) obj = new LogLikelihood(g, robust);
+  else if (obj_kind == 1) obj = new Hamming(g, VectorXf(Eigen::Map<const VectorXf>(cw, ncw)));
+  else obj = new IntersectionOverUnion(g);
+  VectorXf ug, lg, kg;
+  double r = m->crf->gradient(n_iter, *obj, unary_grad ? &ug : 0, lbl_cmp_grad ? &lg : 0, kernel_grad ? &kg : 0);
+  delete obj;
+  if (unary_grad && ug.rows()) std::memcpy(unary_grad, ug.data(), sizeof(float) * ug.rows());
+  if (lbl_cmp_grad && lg.rows()) std::memcpy(lbl_cmp_grad, lg.data(), sizeof(float) * lg.rows());
+  if (kernel_grad && kg.rows()) std::memcpy(kernel_grad, kg.data(), sizeof(float) * kg.rows());
+  return r;
+}
+// Hamming(gt, class_weight_pow)'s class weights (objective.cpp:51-63): the class keeps them private, so they are read
+// back through evaluate() on a Q of ones (d_mul_Q(gt_i, i) = class_weight[gt_i])
+void ref_hamming_weights(const short* gt, int N, float pw, int L, float* out_L) {
+  VectorXs g = Eigen::Map<const VectorXs>(gt, N);
+  Hamming hm(g, pw);
+  MatrixXf Q = MatrixXf::Ones(L, N), d;
+  hm.evaluate(d, Q);
+  for (int l = 0; l < L; l++) out_L[l] = 0.f;
+  for (int i = 0; i < N; i++)
+    if (gt[i] >= 0 && gt[i] < L) out_L[gt[i]] = d(gt[i], i);
 }
 const char* ref_describe() { return "reference C++ compiled from /root/reference (g++ -O2 -DNDEBUG, SSE2)"; }
 }

@@ -77,6 +77,17 @@ cdef extern from "dcrf_b200.h" nogil:
     int dcrf_pairwise_apply(dcrf_t* m, int k, dcrf_mat_t* Q, dcrf_mat_t** out)
     int dcrf_pairwise_apply_transpose(dcrf_t* m, int k, dcrf_mat_t* Q, dcrf_mat_t** out)
     int dcrf_lattice_gradient(dcrf_t* m, int k, const float* a, const float* b, int L, float* df)
+    ctypedef struct dcrf_objective:
+        int kind
+        const int16_t* gt
+        float robust
+        const float* class_weight
+        int n_class_weight
+    int dcrf_gradient(dcrf_t* m, int n_iterations, const dcrf_objective* objective, double* value, float* unary_grad,
+                      float* lbl_cmp_grad, float* kernel_grad)
+    int dcrf_num_parameters(dcrf_t* m, int group, int* n)
+    int dcrf_get_parameters(dcrf_t* m, int group, float* out)
+    int dcrf_set_parameters(dcrf_t* m, int group, const float* v, int n)
     int dcrf_set_iteration_mode(dcrf_t* m, int mode)
     int dcrf_set_softmax_mode(dcrf_t* m, int fast)
     int dcrf_set_kernel_variant(dcrf_t* m, int mask)
@@ -892,6 +903,127 @@ cdef class DenseCRF:
             st = dcrf_lattice_gradient(self._h, k, &a_NxL[0, 0], &b_NxL[0, 0], L, &o[0, 0])
         _check(st)
         return out
+
+
+    # ---- learning path (densecrf.h:106-124; not wrapped by the reference's densecrf.pyx) ------------------------------
+    def _get_params(self, int group):
+        import numpy as np
+        cdef int n = 0
+        _check(dcrf_num_parameters(self._h, group, &n))
+        out = np.zeros(n, np.float32)
+        cdef float[::1] o = out
+        if n > 0:
+            _check(dcrf_get_parameters(self._h, group, &o[0]))
+        return out
+
+    def _set_params(self, int group, v):
+        import numpy as np
+        arr = np.ascontiguousarray(v, dtype=np.float32).ravel()
+        cdef float[::1] a = arr
+        cdef int n = <int>arr.shape[0], st
+        cdef const float* p = &a[0] if n > 0 else NULL
+        with nogil:
+            st = dcrf_set_parameters(self._h, group, p, n)
+        _check(st)
+
+    def unaryParameters(self):
+        """DenseCRF::unaryParameters (densecrf.cpp:298-302)."""
+        return self._get_params(0)
+
+    def setUnaryParameters(self, v):
+        self._set_params(0, v)
+
+    def labelCompatibilityParameters(self):
+        """DenseCRF::labelCompatibilityParameters (densecrf.cpp:307-320)."""
+        return self._get_params(1)
+
+    def setLabelCompatibilityParameters(self, v):
+        self._set_params(1, v)
+
+    def kernelParameters(self):
+        """DenseCRF::kernelParameters (densecrf.cpp:335-348)."""
+        return self._get_params(2)
+
+    def setKernelParameters(self, v):
+        """DenseCRF::setKernelParameters (densecrf.cpp:349-363): every DIAG / FULL kernel rebuilds its lattice."""
+        self._set_params(2, v)
+
+    def gradient(self, int n_iterations, objective, bint unary=True, bint label_compatibility=True, bint kernel=True):
+        """DenseCRF::gradient (densecrf.cpp:237-297): (objective value, unary_grad, lbl_cmp_grad, kernel_grad) after
+        n_iterations of mean field; a gradient that was not asked for (or whose parameter vector is empty) comes back
+        as an empty array.  `objective` is a LogLikelihood, Hamming or IntersectionOverUnion."""
+        import numpy as np
+        cdef Objective ob = objective
+        cdef dcrf_objective o
+        cdef int16_t[::1] gt = ob.gt
+        if gt.shape[0] != self._nvar:
+            raise ValueError("the objective's ground truth has {} entries, the model {} variables".format(gt.shape[0], self._nvar))
+        cdef float[::1] cw = ob.class_weight
+        o.kind = ob.kind
+        o.gt = &gt[0]
+        o.robust = ob.robust
+        o.class_weight = &cw[0] if cw.shape[0] > 0 else NULL
+        o.n_class_weight = <int>cw.shape[0]
+        gu = np.zeros(len(self._get_params(0)) if unary else 0, np.float32)
+        gl = np.zeros(len(self._get_params(1)) if label_compatibility else 0, np.float32)
+        gk = np.zeros(len(self._get_params(2)) if kernel else 0, np.float32)
+        cdef float[::1] vu = gu, vl = gl, vk = gk
+        cdef float* pu = &vu[0] if gu.shape[0] > 0 else NULL
+        cdef float* pl = &vl[0] if gl.shape[0] > 0 else NULL
+        cdef float* pk = &vk[0] if gk.shape[0] > 0 else NULL
+        cdef double value = 0
+        cdef int st
+        with nogil:
+            st = dcrf_gradient(self._h, n_iterations, &o, &value, pu, pl, pk)
+        _check(st)
+        return value, gu, gl, gk
+
+
+cdef class Objective:
+    """ObjectiveFunction (objective.h:31-36): what DenseCRF.gradient evaluates on the last Q."""
+    cdef int kind
+    cdef float robust
+    cdef object gt            # int16 (N,)
+    cdef object class_weight  # float32
+
+    def _init(self, int kind, gt, float robust, w):
+        import numpy as np
+        self.kind = kind
+        self.gt = np.ascontiguousarray(gt, dtype=np.int16).ravel()
+        self.robust = robust
+        self.class_weight = np.ascontiguousarray(w, dtype=np.float32).ravel()
+
+
+cdef class LogLikelihood(Objective):
+    """LogLikelihood(gt, robust=0) (objective.h:38-46, objective.cpp:35-50)."""
+    def __init__(self, gt, float robust=0):
+        self._init(0, gt, robust, [])
+
+
+cdef class Hamming(Objective):
+    """Hamming(gt, class_weight_pow=0) or Hamming(gt, class_weights) (objective.h:48-57, objective.cpp:51-80)."""
+    def __init__(self, gt, class_weight=0.0):
+        import numpy as np
+        g = np.ascontiguousarray(gt, dtype=np.int16).ravel()
+        if np.ndim(class_weight) == 0:
+            # objective.cpp:51-63, in the reference's float arithmetic
+            M = max(int(g.max()) + 1, 0) if g.size else 0
+            cnt = np.bincount(g[g >= 0], minlength=M).astype(np.float32)
+            w = cnt / cnt.sum(dtype=np.float32)
+            w = np.power(w, np.float32(-float(class_weight)), dtype=np.float32)
+            w = w / (cnt * w).sum(dtype=np.float32)
+            class_weight = w
+        self._init(1, g, 0, class_weight)
+
+    @property
+    def class_weights(self):
+        return self.class_weight
+
+
+cdef class IntersectionOverUnion(Objective):
+    """IntersectionOverUnion(gt) (objective.h:59-66, objective.cpp:81-109)."""
+    def __init__(self, gt):
+        self._init(2, gt, 0, [])
 
 
 cdef class DenseCRF2D(DenseCRF):

@@ -342,6 +342,14 @@ struct Term {
   float* msg = nullptr;                    // N x Lp message of this term (tensor-core update path only)
   float* qn = nullptr;                     // N x Lp: Q * diag(norm), written by the update kernel for this term's next splat
   size_t val_bytes = 0;
+  // learning path (DenseKernel's f_, ktype_, parameters_; pairwise.cpp:35-39): where the features came from, kept for
+  // DIAG_KERNEL / FULL_KERNEL terms so that kernelParameters / kernelGradient can form f_ when they are first asked for
+  int ktype = DCRF_CONST_KERNEL, d = 0;
+  FeatureSource src{};
+  void* src_buf = nullptr;       // the device buffer src points into (features / image), owned by the term
+  float* feat0 = nullptr;        // f_: d x N row-major, materialised on first use
+  std::vector<float> compat_host;  // Potts: [w]; Diagonal: L; Matrix: L x L symmetrised, row-major (parameters())
+  std::vector<float> kparams;    // parameters_ (DIAG: d, FULL: d*d column-major); empty = never set (ones / identity)
   bool pre() const { return ntype == DCRF_NORMALIZE_SYMMETRIC || ntype == DCRF_NORMALIZE_BEFORE; }
   bool post() const { return ntype == DCRF_NORMALIZE_SYMMETRIC || ntype == DCRF_NORMALIZE_AFTER; }
 };
@@ -353,6 +361,11 @@ struct dcrf_model {
   cudaStream_t stream = nullptr;
   Profiler prof;
   float* U = nullptr;  // N x Lp, null = no unary set
+  // LogisticUnaryEnergy (unary.cpp:47-71) keeps its two factors for parameters() / gradient(): L_ on the host (L x F
+  // row-major), f_ on the device (F x N row-major).  A constant unary has neither.
+  std::vector<float> ulog_L;
+  float* ulog_f = nullptr;
+  int ulog_F = 0;
   std::vector<Term*> terms;
   float* acc = nullptr;  // staged path: running tmp1
   float* msg = nullptr;  // staged path / KL: one message
@@ -455,7 +468,8 @@ dcrf_model* model_new(int N, int L, int W, int H, int device) {
 void term_free(dcrf_model* m, Term* t) {
   cudaStream_t s = m->stream;
   if (!t->shared) t->lat.release(s);
-  for (void* p : {(void*)t->norm, (void*)t->diag, (void*)t->Wm, (void*)t->Whi, (void*)t->Wlo, (void*)t->valA, (void*)t->msg, (void*)t->qn})
+  for (void* p : {(void*)t->norm, (void*)t->diag, (void*)t->Wm, (void*)t->Whi, (void*)t->Wlo, (void*)t->valA, (void*)t->msg, (void*)t->qn,
+                  t->src_buf, (void*)t->feat0})
     dev_free(p, s);
   delete t;
 }
@@ -1082,78 +1096,103 @@ std::shared_ptr<SharedLattice> shared_gaussian_lattice(dcrf_model* m, const Feat
   return sp;
 }
 
-void add_term(dcrf_model* m, const FeatureSource& src, int d, int compat_kind, const float* compat, int ktype,
-              int ntype) {
+// DenseKernel::initLattice (pairwise.cpp:40-62): the lattice of `src` and the normalisation vector of t->ntype
+void term_init_lattice(dcrf_model* m, Term* t, const FeatureSource& src, int d) {
+  Ctx cx = m->cx();
+  cudaStream_t s = m->stream;
+  if (src.kind == FEAT_GAUSS2D) {
+    t->shared = shared_gaussian_lattice(m, src);
+    t->lat = t->shared->lat;  // pointers only; owned by the shared object
+  } else {
+    lattice_build(cx, src, d, m->N, &t->lat, m->npi);
+  }
+  const int N = m->N, ntype = t->ntype;
+  if (t->shared) {
+    t->norm = dev_alloc<float>(N, s);
+    DCRF_CUDA(cudaMemcpyAsync(t->norm, t->shared->norm_raw, (size_t)N * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  } else {
+    t->norm = raw_norm(m, t->lat);
+  }
+  if (ntype == DCRF_NO_NORMALIZATION) {
+    // mean_norm = N / sum(norm): the reference adds N floats one after the other in float
+    // (pairwise.cpp:47-51); that rounding sequence is inherently serial, so it runs on the host once
+    std::vector<float> h(N);
+    DCRF_CUDA(cudaMemcpyAsync(h.data(), t->norm, (size_t)N * sizeof(float), cudaMemcpyDeviceToHost, s));
+    DCRF_CUDA(cudaStreamSynchronize(s));
+    const int per = m->npi > 0 ? m->npi : N;  // a batch: every image has its own mean, as separate models would
+    for (int i0 = 0; i0 < N; i0 += per) {
+      float mean = 0.f;
+      for (int i = i0; i < i0 + per; i++) mean += h[i];
+      mean = (float)per / mean;
+      launch_fill(cx, t->norm + i0, per, mean);
+    }
+  } else {
+    launch_norm_transform(cx, N, t->norm, ntype == DCRF_NORMALIZE_SYMMETRIC);
+  }
+  DCRF_CUDA(cudaGetLastError());
+  DCRF_CUDA(cudaStreamSynchronize(s));
+}
+
+// LabelCompatibility of a term from its host description (labelcompatibility.cpp:43, :63, :76); replaces what was there
+void term_set_compat(dcrf_model* m, Term* t, int compat_kind, const float* compat) {
+  Ctx cx = m->cx();
+  cudaStream_t s = m->stream;
+  const int L = m->L, Lp = m->rl.Lp;
+  t->ckind = compat_kind;
+  if (compat_kind == DCRF_COMPAT_POTTS) {
+    t->potts_w = compat[0];
+    t->compat_host.assign(1, compat[0]);
+  } else if (compat_kind == DCRF_COMPAT_DIAGONAL) {
+    std::vector<float> w(Lp, 0.f);
+    std::copy(compat, compat + L, w.begin());
+    t->compat_host.assign(compat, compat + L);
+    if (!t->diag) t->diag = dev_alloc<float>(Lp, s);
+    DCRF_CUDA(cudaMemcpyAsync(t->diag, w.data(), Lp * sizeof(float), cudaMemcpyHostToDevice, s));
+    DCRF_CUDA(cudaStreamSynchronize(s));
+  } else {
+    std::vector<float> w((size_t)L * L);
+    for (int a = 0; a < L; a++)
+      for (int b = 0; b < L; b++) w[(size_t)a * L + b] = 0.5f * (compat[(size_t)a * L + b] + compat[(size_t)b * L + a]);
+    t->compat_host = w;
+    if (!t->Wm) t->Wm = dev_alloc<float>((size_t)L * L, s);
+    DCRF_CUDA(cudaMemcpyAsync(t->Wm, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+    if (matrix_tc_supported(m->rl)) {
+      int Np, Kp;
+      matrix_tc_dims(m->rl, &Np, &Kp);
+      if (!t->Whi) t->Whi = dev_alloc<float>((size_t)Np * Kp, s);
+      if (!t->Wlo) t->Wlo = dev_alloc<float>((size_t)Np * Kp, s);
+      launch_split_w(cx, m->rl, t->Wm, t->Whi, t->Wlo);
+    }
+    DCRF_CUDA(cudaStreamSynchronize(s));
+  }
+}
+
+// returns true when the term took ownership of `src_buf` (the device buffer `src` points into): DIAG_KERNEL / FULL_KERNEL
+// terms keep their feature source for the learning path, CONST_KERNEL terms have no kernel parameters
+bool add_term(dcrf_model* m, const FeatureSource& src, int d, int compat_kind, const float* compat, int ktype,
+              int ntype, void* src_buf = nullptr) {
   DCRF_REQUIRE(ntype >= 0 && ntype <= 3, "bad NormalizationType");
   DCRF_REQUIRE(ktype >= 0 && ktype <= 2, "bad KernelType");  // no effect on inference (pairwise.cpp:116-121)
   DCRF_REQUIRE(compat_kind >= 0 && compat_kind <= 2 && compat, "bad label compatibility");
-  Ctx cx = m->cx();
-  cudaStream_t s = m->stream;
   Term* t = new Term();
   try {
-    if (src.kind == FEAT_GAUSS2D) {
-      t->shared = shared_gaussian_lattice(m, src);
-      t->lat = t->shared->lat;  // pointers only; owned by the shared object
-    } else {
-      lattice_build(cx, src, d, m->N, &t->lat, m->npi);
-    }
     t->ntype = ntype;
-    t->ckind = compat_kind;
-    const int L = m->L, Lp = m->rl.Lp;
-    if (compat_kind == DCRF_COMPAT_POTTS) {
-      t->potts_w = compat[0];
-    } else if (compat_kind == DCRF_COMPAT_DIAGONAL) {
-      std::vector<float> w(Lp, 0.f);
-      std::copy(compat, compat + L, w.begin());
-      t->diag = dev_alloc<float>(Lp, s);
-      DCRF_CUDA(cudaMemcpyAsync(t->diag, w.data(), Lp * sizeof(float), cudaMemcpyHostToDevice, s));
-      DCRF_CUDA(cudaStreamSynchronize(s));
-    } else {
-      std::vector<float> w((size_t)L * L);
-      for (int a = 0; a < L; a++)
-        for (int b = 0; b < L; b++) w[(size_t)a * L + b] = 0.5f * (compat[(size_t)a * L + b] + compat[(size_t)b * L + a]);
-      t->Wm = dev_alloc<float>((size_t)L * L, s);
-      DCRF_CUDA(cudaMemcpyAsync(t->Wm, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice, s));
-      if (matrix_tc_supported(m->rl)) {
-        int Np, Kp;
-        matrix_tc_dims(m->rl, &Np, &Kp);
-        t->Whi = dev_alloc<float>((size_t)Np * Kp, s);
-        t->Wlo = dev_alloc<float>((size_t)Np * Kp, s);
-        launch_split_w(cx, m->rl, t->Wm, t->Whi, t->Wlo);
-      }
-      DCRF_CUDA(cudaStreamSynchronize(s));
-    }
-    const int N = m->N;
-    if (t->shared) {
-      t->norm = dev_alloc<float>(N, s);
-      DCRF_CUDA(cudaMemcpyAsync(t->norm, t->shared->norm_raw, (size_t)N * sizeof(float), cudaMemcpyDeviceToDevice, s));
-    } else {
-      t->norm = raw_norm(m, t->lat);
-    }
-    if (ntype == DCRF_NO_NORMALIZATION) {
-      // mean_norm = N / sum(norm): the reference adds N floats one after the other in float
-      // (pairwise.cpp:47-51); that rounding sequence is inherently serial, so it runs on the host once
-      std::vector<float> h(N);
-      DCRF_CUDA(cudaMemcpyAsync(h.data(), t->norm, (size_t)N * sizeof(float), cudaMemcpyDeviceToHost, s));
-      DCRF_CUDA(cudaStreamSynchronize(s));
-      const int per = m->npi > 0 ? m->npi : N;  // a batch: every image has its own mean, as separate models would
-      for (int i0 = 0; i0 < N; i0 += per) {
-        float mean = 0.f;
-        for (int i = i0; i < i0 + per; i++) mean += h[i];
-        mean = (float)per / mean;
-        launch_fill(cx, t->norm + i0, per, mean);
-      }
-    } else {
-      launch_norm_transform(cx, N, t->norm, ntype == DCRF_NORMALIZE_SYMMETRIC);
-    }
-    DCRF_CUDA(cudaGetLastError());
-    DCRF_CUDA(cudaStreamSynchronize(s));
+    t->ktype = ktype;
+    t->d = d;
+    term_init_lattice(m, t, src, d);
+    term_set_compat(m, t, compat_kind, compat);
   } catch (...) {
     term_free(m, t);
     throw;
   }
+  const bool adopt = ktype != DCRF_CONST_KERNEL;
+  if (adopt) {
+    t->src = src;
+    t->src_buf = src_buf;
+  }
   m->terms.push_back(t);
   m->drop_graphs();
+  return adopt;
 }
 
 dcrf_mat* new_result_mat(dcrf_model* m) {
@@ -1201,7 +1240,7 @@ void dcrf_destroy(dcrf_t* m) {
     DeviceGuard g(m->device);
     cudaStreamSynchronize(m->stream);
     for (Term* t : m->terms) term_free(m, t);
-    for (void* p : {(void*)m->U, (void*)m->acc, (void*)m->msg, (void*)m->kl_sums, (void*)m->flush_buf}) dev_free(p, m->stream);
+    for (void* p : {(void*)m->U, (void*)m->acc, (void*)m->msg, (void*)m->kl_sums, (void*)m->flush_buf, (void*)m->ulog_f}) dev_free(p, m->stream);
     cudaStreamSynchronize(m->stream);
     m->drop_graphs();
     for (cudaStream_t s2 : m->aux) cudaStreamDestroy(s2);
@@ -1216,10 +1255,18 @@ void dcrf_destroy(dcrf_t* m) {
   delete m;
 }
 
+// a new unary replaces the old one (densecrf.cpp:88-96): a logistic unary's factors go with it
+static void forget_logistic(dcrf_model* m) {
+  if (m->ulog_f) dev_free(m->ulog_f, m->stream);
+  m->ulog_f = nullptr;
+  m->ulog_F = 0;
+  m->ulog_L.clear();
+}
 dcrf_status dcrf_set_unary_const(dcrf_t* m, const float* u_LxN) {
   return guarded([&] {
     DCRF_REQUIRE(m && u_LxN, "null argument");
     DeviceGuard g(m->device);
+    forget_logistic(m);
     const size_t n = (size_t)m->N * m->L;
     float* planes = upload_tmp(m, u_LxN, n * sizeof(float));
     if (!m->U) {
@@ -1236,6 +1283,7 @@ dcrf_status dcrf_set_unary_device(dcrf_t* m, const float* dev_u_LxN) {
   return guarded([&] {
     DCRF_REQUIRE(m && dev_u_LxN, "null argument");
     DeviceGuard g(m->device);
+    forget_logistic(m);
     cudaPointerAttributes at{};
     DCRF_CUDA(cudaPointerGetAttributes(&at, dev_u_LxN));
     DCRF_REQUIRE(at.type == cudaMemoryTypeDevice && at.device == m->device,
@@ -1256,6 +1304,7 @@ dcrf_status dcrf_set_unary_from_softmax(dcrf_t* m, const float* sm_LxN, double s
     DCRF_REQUIRE(m && sm_LxN, "null argument");
     DCRF_REQUIRE(!(scale > 1.0), "`scale` needs to be in (0,1]");
     DeviceGuard g(m->device);
+    forget_logistic(m);
     const size_t n = (size_t)m->N * m->L;
     float* planes = upload_tmp(m, sm_LxN, n * sizeof(float));
     if (!m->U) {
@@ -1280,7 +1329,10 @@ dcrf_status dcrf_set_unary_logistic(dcrf_t* m, const float* Lmat_LxF, int F, con
     }
     launch_logistic_unary(m->cx(), m->rl, m->N, F, dL, df, m->U);
     dev_free(dL, m->stream);
-    dev_free(df, m->stream);
+    forget_logistic(m);
+    m->ulog_f = df;  // kept: LogisticUnaryEnergy::gradient multiplies by f_ (unary.cpp:67-71)
+    m->ulog_F = F;
+    m->ulog_L.assign(Lmat_LxF, Lmat_LxF + (size_t)m->L * F);
     DCRF_CUDA(cudaGetLastError());
     DCRF_CUDA(cudaStreamSynchronize(m->stream));
   });
@@ -1296,13 +1348,14 @@ dcrf_status dcrf_add_pairwise_energy(dcrf_t* m, const float* feat_dxN, int d, in
     FeatureSource src{};
     src.kind = FEAT_GENERIC;
     src.feat = f;
+    bool kept = false;
     try {
-      add_term(m, src, d, compat_kind, compat_data, kernel_type, norm_type);
+      kept = add_term(m, src, d, compat_kind, compat_data, kernel_type, norm_type, f);
     } catch (...) {
       dev_free(f, m->stream);
       throw;
     }
-    dev_free(f, m->stream);
+    if (!kept) dev_free(f, m->stream);
   });
 }
 dcrf_status dcrf_add_pairwise_gaussian(dcrf_t* m, float sx, float sy, int compat_kind, const float* compat_data,
@@ -1333,13 +1386,14 @@ dcrf_status dcrf_add_pairwise_bilateral(dcrf_t* m, float sx, float sy, float sr,
     src.H = m->npi > 0 ? m->npi / m->W : 0;
     src.rgb = im;
     src.s[0] = sx, src.s[1] = sy, src.s[2] = sr, src.s[3] = sg, src.s[4] = sb;
+    bool kept = false;
     try {
-      add_term(m, src, 5, compat_kind, compat_data, kernel_type, norm_type);
+      kept = add_term(m, src, 5, compat_kind, compat_data, kernel_type, norm_type, im);
     } catch (...) {
       dev_free(im, m->stream);
       throw;
     }
-    dev_free(im, m->stream);
+    if (!kept) dev_free(im, m->stream);
   });
 }
 
@@ -1373,13 +1427,14 @@ dcrf_status dcrf_add_pairwise_nd(dcrf_t* m, int nsp, const int* dims, const floa
       dimg = upload_tmp(m, img, (size_t)m->N * nch * (img_is_float ? 4 : 1));
       src.img = dimg;
     }
+    bool kept = false;
     try {
-      add_term(m, src, nsp + nch, compat_kind, compat_data, kernel_type, norm_type);
+      kept = add_term(m, src, nsp + nch, compat_kind, compat_data, kernel_type, norm_type, dimg);
     } catch (...) {
       dev_free(dimg, m->stream);
       throw;
     }
-    dev_free(dimg, m->stream);
+    if (!kept) dev_free(dimg, m->stream);
   });
 }
 
@@ -1808,11 +1863,11 @@ struct BatchChunk {
     src.kind = FEAT_GAUSS2D;
     src.W = p.W, src.H = p.H;
     src.s[0] = p.g_sx, src.s[1] = p.g_sy;
-    add_term(m, src, 2, DCRF_COMPAT_POTTS, &p.g_w, 1, DCRF_NORMALIZE_SYMMETRIC);
+    add_term(m, src, 2, DCRF_COMPAT_POTTS, &p.g_w, DCRF_CONST_KERNEL, DCRF_NORMALIZE_SYMMETRIC);  // no learning path on batch chunks
     src.kind = FEAT_BILATERAL2D;
     src.rgb = im;
     src.s[0] = p.b_sx, src.s[1] = p.b_sy, src.s[2] = p.b_sr, src.s[3] = p.b_sg, src.s[4] = p.b_sb;
-    add_term(m, src, 5, DCRF_COMPAT_POTTS, &p.b_w, 1, DCRF_NORMALIZE_SYMMETRIC);
+    add_term(m, src, 5, DCRF_COMPAT_POTTS, &p.b_w, DCRF_CONST_KERNEL, DCRF_NORMALIZE_SYMMETRIC);
     dev_free(im, s);
     im = nullptr;
   }
@@ -2199,6 +2254,404 @@ dcrf_status dcrf_lattice_gradient(dcrf_t* m, int k, const float* a_NxL, const fl
     DCRF_CUDA(cudaStreamSynchronize(s));
   });
 }
+// ---- learning path: parameter vectors and DenseCRF::gradient ------------------------------------------------------
+namespace {
+int n_compat_params(const dcrf_model* m, const Term* t) {
+  return t->ckind == DCRF_COMPAT_POTTS ? 1 : t->ckind == DCRF_COMPAT_DIAGONAL ? m->L : m->L * (m->L + 1) / 2;
+}
+int n_kernel_params(const Term* t) {
+  return t->ktype == DCRF_CONST_KERNEL ? 0 : t->ktype == DCRF_DIAG_KERNEL ? t->d : t->d * t->d;
+}
+int n_params(const dcrf_model* m, int group) {
+  int n = 0;
+  if (group == DCRF_PARAMS_UNARY) return (int)m->ulog_L.size();
+  for (const Term* t : m->terms) n += group == DCRF_PARAMS_LABEL_COMPATIBILITY ? n_compat_params(m, t) : n_kernel_params(t);
+  return n;
+}
+// f_ of the term's DenseKernel, d x N row-major
+const float* term_features(dcrf_model* m, Term* t) {
+  if (!t->feat0) {
+    DCRF_REQUIRE(t->ktype != DCRF_CONST_KERNEL, "a CONST_KERNEL term keeps no features");
+    t->feat0 = dev_alloc<float>((size_t)t->d * m->N, m->stream);
+    materialize_features(m->cx(), t->src, t->d, m->N, 0, nullptr, t->feat0);
+  }
+  return t->feat0;
+}
+// DenseKernel::setParameters (pairwise.cpp:139-151): initLattice(P * f_)
+void term_set_kernel_params(dcrf_model* m, Term* t, const float* v) {
+  const int d = t->d, N = m->N, np = n_kernel_params(t);
+  if (np == 0) return;
+  cudaStream_t s = m->stream;
+  const float* f0 = term_features(m, t);
+  float* dp = upload_tmp(m, v, (size_t)np * sizeof(float));
+  float* tf = dev_alloc<float>((size_t)d * N, s);
+  FeatureSource g{};
+  g.kind = FEAT_GENERIC;
+  g.feat = f0;
+  materialize_features(m->cx(), g, d, N, t->ktype, dp, tf);
+  DCRF_CUDA(cudaStreamSynchronize(s));  // nothing queued may still read the old lattice
+  for (cudaStream_t a : m->aux) DCRF_CUDA(cudaStreamSynchronize(a));
+  if (!t->shared) t->lat.release(s);
+  t->shared.reset();
+  t->lat = Lattice();
+  dev_free(t->norm, s);
+  dev_free(t->valA, s);
+  t->norm = nullptr, t->valA = t->valB = nullptr, t->val_bytes = 0;
+  g.feat = tf;
+  try {
+    term_init_lattice(m, t, g, d);
+  } catch (...) {
+    dev_free(dp, s);
+    dev_free(tf, s);
+    throw;
+  }
+  dev_free(dp, s);
+  dev_free(tf, s);
+  t->kparams.assign(v, v + np);
+  m->drop_graphs();
+}
+// Permutohedral::compute(x, reverse) of the term's lattice on device rows (no normalisation, no compatibility)
+void term_compute(dcrf_model* m, Term* t, const float* x, bool reverse, float* out) {
+  Ctx cx = m->cx();
+  const float* fin = run_filter(cx, t->lat, m->rl, x, nullptr, t->valA, t->valB, reverse);
+  launch_slice(cx, t->lat, m->rl, fin, nullptr, nullptr, SLICE_WRITE, nullptr, false, out);
+}
+struct GradScratch {  // N x Lp buffers of the backward pass
+  float *an, *bn, *fa, *fb, *rin, *ones, *df, *dr;
+};
+// DenseKernel::featureGradient (pairwise.cpp:87-116) into w.df (N x d)
+void term_feature_gradient(dcrf_model* m, Term* t, const float* a, const float* b, GradScratch& w) {
+  Ctx cx = m->cx();
+  const RowLayout rl = m->rl;
+  const int N = m->N;
+  if (t->ntype == DCRF_NO_NORMALIZATION) {
+    lattice_gradient(cx, t->lat, rl, a, b, t->valA, t->valB, w.df);
+    return;
+  }
+  const float *ka = a, *kb = b;  // arguments of the second kernelGradient
+  if (t->ntype == DCRF_NORMALIZE_SYMMETRIC) {
+    launch_scale_rows(cx, rl, N, a, t->norm, w.an);
+    launch_scale_rows(cx, rl, N, b, t->norm, w.bn);
+    term_compute(m, t, w.an, true, w.fa);
+    term_compute(m, t, w.bn, false, w.fb);
+    ka = w.an, kb = w.bn;
+  } else if (t->ntype == DCRF_NORMALIZE_AFTER) {
+    term_compute(m, t, b, false, w.fb);
+    launch_scale_rows(cx, rl, N, a, t->norm, w.an);
+    ka = w.an;
+  } else {
+    term_compute(m, t, a, true, w.fa);
+    launch_scale_rows(cx, rl, N, b, t->norm, w.bn);
+    kb = w.bn;
+  }
+  launch_feature_gradient_input(cx, rl, N, t->ntype, a, w.fb, w.fa, b, t->norm, w.rin);
+  lattice_gradient(cx, t->lat, rl, w.rin, w.ones, t->valA, t->valB, w.dr);
+  lattice_gradient(cx, t->lat, rl, ka, kb, t->valA, t->valB, w.df);
+  launch_neg_add(cx, (size_t)N * t->lat.d, w.dr, w.df);
+}
+}  // namespace
+
+dcrf_status dcrf_num_parameters(dcrf_t* m, int group, int* n) {
+  return guarded([&] {
+    DCRF_REQUIRE(m && n && group >= 0 && group <= 2, "bad argument");
+    *n = n_params(m, group);
+  });
+}
+dcrf_status dcrf_get_parameters(dcrf_t* m, int group, float* out) {
+  return guarded([&] {
+    DCRF_REQUIRE(m && group >= 0 && group <= 2, "bad argument");
+    if (n_params(m, group) == 0) return;
+    DCRF_REQUIRE(out, "null argument");
+    const int L = m->L;
+    if (group == DCRF_PARAMS_UNARY) {
+      const int F = m->ulog_F;
+      for (int l = 0; l < L; l++)
+        for (int f = 0; f < F; f++) out[l + (size_t)L * f] = m->ulog_L[(size_t)l * F + f];
+      return;
+    }
+    for (const Term* t : m->terms) {
+      if (group == DCRF_PARAMS_LABEL_COMPATIBILITY) {
+        if (t->ckind != DCRF_COMPAT_MATRIX) {
+          out = std::copy(t->compat_host.begin(), t->compat_host.end(), out);
+        } else {
+          for (int i = 0; i < L; i++)
+            for (int j = i; j < L; j++) *out++ = t->compat_host[(size_t)i * L + j];
+        }
+      } else {
+        const int np = n_kernel_params(t), d = t->d;
+        if (!t->kparams.empty()) {
+          out = std::copy(t->kparams.begin(), t->kparams.end(), out);
+        } else {
+          for (int e = 0; e < np; e++) *out++ = (t->ktype == DCRF_DIAG_KERNEL || e % d == e / d) ? 1.f : 0.f;
+        }
+      }
+    }
+  });
+}
+dcrf_status dcrf_set_parameters(dcrf_t* m, int group, const float* v, int n) {
+  return guarded([&] {
+    DCRF_REQUIRE(m && group >= 0 && group <= 2, "bad argument");
+    DCRF_REQUIRE(n == n_params(m, group), "this model has " + std::to_string(n_params(m, group)) + " parameters of that group, got " +
+                                              std::to_string(n));
+    if (n == 0) return;
+    DCRF_REQUIRE(v, "null argument");
+    DeviceGuard g(m->device);
+    const int L = m->L;
+    DCRF_CUDA(cudaStreamSynchronize(m->stream));
+    if (group == DCRF_PARAMS_UNARY) {
+      const int F = m->ulog_F;
+      for (int l = 0; l < L; l++)
+        for (int f = 0; f < F; f++) m->ulog_L[(size_t)l * F + f] = v[l + (size_t)L * f];
+      float* dL = upload_tmp(m, m->ulog_L.data(), m->ulog_L.size() * sizeof(float));
+      launch_logistic_unary(m->cx(), m->rl, m->N, F, dL, m->ulog_f, m->U);
+      dev_free(dL, m->stream);
+      DCRF_CUDA(cudaGetLastError());
+      DCRF_CUDA(cudaStreamSynchronize(m->stream));
+      return;
+    }
+    for (Term* t : m->terms) {
+      if (group == DCRF_PARAMS_LABEL_COMPATIBILITY) {
+        const int np = n_compat_params(m, t);
+        if (t->ckind != DCRF_COMPAT_MATRIX) {
+          term_set_compat(m, t, t->ckind, v);
+        } else {
+          std::vector<float> w((size_t)L * L);
+          int k = 0;
+          for (int i = 0; i < L; i++)
+            for (int j = i; j < L; j++, k++) w[(size_t)i * L + j] = w[(size_t)j * L + i] = v[k];
+          term_set_compat(m, t, t->ckind, w.data());
+        }
+        v += np;
+      } else {
+        term_set_kernel_params(m, t, v);
+        v += n_kernel_params(t);
+      }
+    }
+    m->drop_graphs();  // Potts weights are launch arguments of the captured kernels
+    DCRF_CUDA(cudaGetLastError());
+    DCRF_CUDA(cudaStreamSynchronize(m->stream));
+  });
+}
+
+dcrf_status dcrf_gradient(dcrf_t* m, int n_iterations, const dcrf_objective* obj, double* value, float* unary_grad,
+                          float* lbl_cmp_grad, float* kernel_grad) {
+  return guarded([&] {
+    DCRF_REQUIRE(m && obj && obj->gt && value, "null argument");
+    DCRF_REQUIRE(n_iterations >= 0, "negative iteration count");
+    DCRF_REQUIRE(obj->kind >= 0 && obj->kind <= 2, "unknown objective");
+    DeviceGuard g(m->device);
+    Ctx cx = m->cx();
+    cudaStream_t s = m->stream;
+    const RowLayout rl = m->rl;
+    const int N = m->N, L = m->L, Lp = rl.Lp, nt = (int)m->terms.size();
+    const size_t n = (size_t)N * Lp;
+    if (n_params(m, DCRF_PARAMS_UNARY) == 0) unary_grad = nullptr;
+    if (n_params(m, DCRF_PARAMS_LABEL_COMPATIBILITY) == 0) lbl_cmp_grad = nullptr;
+    if (n_params(m, DCRF_PARAMS_KERNEL) == 0) kernel_grad = nullptr;
+    if (obj->kind == DCRF_OBJECTIVE_HAMMING) {
+      DCRF_REQUIRE(obj->class_weight && obj->n_class_weight >= 1, "the Hamming objective needs class weights");
+      for (int i = 0; i < N; i++)
+        DCRF_REQUIRE(obj->gt[i] < 0 || obj->gt[i] >= L || obj->gt[i] < obj->n_class_weight, "class weights do not cover every label of gt");
+    }
+    std::vector<void*> owned;  // every device buffer of this call
+    auto rows = [&]() {
+      float* p = dev_alloc<float>(n, s);
+      owned.push_back(p);
+      return p;
+    };
+    struct Cleanup {
+      std::vector<void*>& v;
+      cudaStream_t s;
+      ~Cleanup() {
+        for (void* p : v) dev_free(p, s);
+      }
+    } cleanup{owned, s};
+
+    // mean field with every Q kept (densecrf.cpp:239-252)
+    for (Term* t : m->terms) ensure_val(m, t);
+    ensure_scratch_if_staged(m);
+    ensure_aux(m, nt);
+    std::vector<float*> Q(n_iterations + 1);
+    Q[0] = rows();
+    mf_init(m, Q[0]);
+    for (int it = 0; it < n_iterations; it++) {
+      Q[it + 1] = rows();
+      DCRF_CUDA(cudaMemcpyAsync(Q[it + 1], Q[it], n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+      mf_step(m, Q[it + 1], true);
+    }
+    const float* Qn = Q[n_iterations];
+
+    // objective value and b = d_mul_Q (densecrf.cpp:255-257)
+    float *b = rows(), *b2 = rows();
+    int16_t* gt = (int16_t*)upload_tmp(m, obj->gt, (size_t)N * sizeof(int16_t));
+    owned.push_back(gt);
+    double* dsc = dev_alloc<double>(2 * (size_t)L + 1, s);
+    owned.push_back(dsc);
+    if (obj->kind != DCRF_OBJECTIVE_IOU) {
+      float* cw = nullptr;
+      if (obj->kind == DCRF_OBJECTIVE_HAMMING) {
+        std::vector<float> w(L, 0.f);
+        std::copy(obj->class_weight, obj->class_weight + std::min(L, obj->n_class_weight), w.begin());
+        cw = upload_tmp(m, w.data(), (size_t)L * sizeof(float));
+        owned.push_back(cw);
+      }
+      launch_objective_point(cx, rl, N, obj->kind, gt, obj->robust, cw, Qn, b, dsc);
+      DCRF_CUDA(cudaMemcpyAsync(value, dsc, sizeof(double), cudaMemcpyDeviceToHost, s));
+      DCRF_CUDA(cudaStreamSynchronize(s));
+    } else {
+      float *in_rows = rows(), *un_rows = rows();
+      const float one = 1.f;
+      float* d_one = upload_tmp(m, &one, sizeof(float));
+      owned.push_back(d_one);
+      launch_iou_rows(cx, rl, N, gt, Qn, in_rows, un_rows);
+      launch_outer_sums(cx, N, in_rows, Lp, 1, L, d_one, 0, 0, 1, false, dsc);
+      launch_outer_sums(cx, N, un_rows, Lp, 1, L, d_one, 0, 0, 1, false, dsc + L);
+      launch_iou_b(cx, rl, N, gt, Qn, dsc, dsc + L, b);
+      std::vector<double> h(2 * (size_t)L);
+      DCRF_CUDA(cudaMemcpyAsync(h.data(), dsc, h.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+      DCRF_CUDA(cudaStreamSynchronize(s));
+      double r = 0;
+      for (int l = 0; l < L; l++) r += h[l] / (h[L + l] + 1e-20);
+      *value = r / L;
+    }
+    launch_sum_and_normalize(cx, rl, N, b, Qn, false, b2);  // sumAndNormalize(b, b, Q[n])  (:258)
+    std::swap(b, b2);
+
+    // one slot of doubles per sum over the variables that the backward pass needs, reduced on the host at the end
+    const int F = m->ulog_F;
+    std::vector<size_t> lbl_slot, ker_slot;
+    size_t total = 0;
+    const size_t un_sz = unary_grad ? (size_t)L * F : 0;
+    const size_t un_slot0 = total;
+    total += un_sz * (n_iterations + 1);
+    for (int it = 0; it < n_iterations; it++)
+      for (Term* t : m->terms) {
+        lbl_slot.push_back(total);
+        if (lbl_cmp_grad) total += t->ckind == DCRF_COMPAT_MATRIX ? (size_t)L * L : (size_t)L;
+        ker_slot.push_back(total);
+        if (kernel_grad) total += n_kernel_params(t);
+      }
+    double* res = dev_alloc<double>(std::max<size_t>(total, 1), s);
+    owned.push_back(res);
+    int un_count = 0;
+    auto unary_gradient = [&]() {  // LogisticUnaryEnergy::gradient: b * f_^T (unary.cpp:67-71)
+      if (unary_grad) launch_outer_sums(cx, N, b, Lp, 1, L, m->ulog_f, 1, (size_t)N, F, false, res + un_slot0 + un_sz * un_count++);
+    };
+    unary_gradient();  // (:261-262)
+
+    float *tmp1 = nullptr, *tmp2 = nullptr, *fQ = nullptr, *lblQ = nullptr;
+    GradScratch w{};
+    if (n_iterations > 0 && nt > 0) {
+      tmp1 = rows(), tmp2 = rows();
+      if (lbl_cmp_grad) fQ = rows();
+      if (kernel_grad) {
+        lblQ = rows();
+        w.an = rows(), w.bn = rows(), w.fa = rows(), w.fb = rows(), w.rin = rows(), w.ones = rows();
+        launch_fill(cx, w.ones, n, 1.0f);
+        int dmax = 1;
+        for (Term* t : m->terms) dmax = std::max(dmax, t->lat.d);
+        w.df = dev_alloc<float>((size_t)N * dmax, s);
+        w.dr = dev_alloc<float>((size_t)N * dmax, s);
+        owned.push_back(w.df);
+        owned.push_back(w.dr);
+      }
+    }
+    // inverse message passing (:268-295)
+    for (int it = n_iterations - 1; it >= 0; it--) {
+      if (nt == 0) {  // tmp1 = 0: b = sumAndNormalize(0, Q) = 0
+        DCRF_CUDA(cudaMemsetAsync(b, 0, n * sizeof(float), s));
+        unary_gradient();
+        continue;
+      }
+      DCRF_CUDA(cudaMemsetAsync(tmp1, 0, n * sizeof(float), s));
+      for (int k = 0; k < nt; k++) {
+        Term* t = m->terms[k];
+        const size_t slot = (size_t)(n_iterations - 1 - it) * nt + k;
+        if (lbl_cmp_grad) {  // compatibility_->gradient(b, kernel_->apply(Q))  (pairwise.cpp:190-195)
+          const bool pre = t->pre(), post = t->post();
+          const float* fin = run_filter(cx, t->lat, rl, Q[it], pre ? t->norm : nullptr, t->valA, t->valB, false);
+          launch_slice(cx, t->lat, rl, fin, post ? t->norm : nullptr, nullptr, SLICE_WRITE, nullptr, false, fQ);
+          launch_outer_sums(cx, N, b, Lp, 1, L, fQ, Lp, 1, L, t->ckind != DCRF_COMPAT_MATRIX, res + lbl_slot[slot]);
+        }
+        if (kernel_grad && t->ktype != DCRF_CONST_KERNEL) {  // kernel_->gradient(b, compatibility_->apply(Q))  (:202-207)
+          if (t->ckind == DCRF_COMPAT_MATRIX) {
+            launch_matrix_compat(cx, rl, N, t->Wm, Q[it], SLICE_WRITE, nullptr, false, lblQ);
+          } else {
+            CompatDev c = compat_of(t);
+            launch_compat_pointwise(cx, rl, N, c, Q[it], lblQ);
+          }
+          term_feature_gradient(m, t, b, lblQ, w);
+          const float* f0 = term_features(m, t);
+          const int d = t->d;
+          if (t->ktype == DCRF_DIAG_KERNEL)  // (f_ .* fg).rowwise().sum()  (pairwise.cpp:157)
+            launch_outer_sums(cx, N, f0, 1, (size_t)N, d, w.df, d, 1, d, true, res + ker_slot[slot]);
+          else  // fg * f_^T  (:159)
+            launch_outer_sums(cx, N, w.df, d, 1, d, f0, 1, (size_t)N, d, false, res + ker_slot[slot]);
+        }
+        term_apply(m, t, b, SLICE_WRITE, false, tmp2, /*transpose=*/true);
+        launch_add_rows(cx, rl, N, tmp2, tmp1);
+      }
+      launch_sum_and_normalize(cx, rl, N, tmp1, Q[it], true, b2);  // (:290)
+      std::swap(b, b2);
+      unary_gradient();
+    }
+    std::vector<double> h(std::max<size_t>(total, 1));
+    DCRF_CUDA(cudaGetLastError());
+    DCRF_CUDA(cudaMemcpyAsync(h.data(), res, h.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+    DCRF_CUDA(cudaStreamSynchronize(s));
+
+    // the reference's float accumulation over iterations and terms, in its order
+    if (unary_grad) {
+      for (size_t e = 0; e < un_sz; e++) unary_grad[e] = 0.f;
+      for (int c = 0; c < un_count; c++)
+        for (int l = 0; l < L; l++)
+          for (int f = 0; f < F; f++) {
+            const float gv = (float)h[un_slot0 + un_sz * c + (size_t)l * F + f];
+            float& o = unary_grad[l + (size_t)L * f];
+            o = c == 0 ? gv : o + gv;
+          }
+    }
+    if (lbl_cmp_grad) std::fill(lbl_cmp_grad, lbl_cmp_grad + n_params(m, DCRF_PARAMS_LABEL_COMPATIBILITY), 0.f);
+    if (kernel_grad) std::fill(kernel_grad, kernel_grad + n_params(m, DCRF_PARAMS_KERNEL), 0.f);
+    for (int it = n_iterations - 1; it >= 0 && nt > 0; it--) {
+      int ip = 0, ik = 0;
+      for (int k = 0; k < nt; k++) {
+        Term* t = m->terms[k];
+        const size_t slot = (size_t)(n_iterations - 1 - it) * nt + k;
+        if (lbl_cmp_grad) {
+          const double* G = h.data() + lbl_slot[slot];
+          float* o = lbl_cmp_grad + ip;
+          if (t->ckind == DCRF_COMPAT_POTTS) {  // -(b .* Q).sum()  (labelcompatibility.cpp:59)
+            double sum = 0;
+            for (int l = 0; l < L; l++) sum += G[l];
+            o[0] += -(float)sum;
+          } else if (t->ckind == DCRF_COMPAT_DIAGONAL) {  // (b .* Q).rowwise().sum()  (:73-75)
+            for (int l = 0; l < L; l++) o[l] += (float)G[l];
+          } else {  // g = b * Q^T; r[k] = g(i,j) + (i != j ? g(j,i) : 0)  (:101-108)
+            int e = 0;
+            for (int i = 0; i < L; i++)
+              for (int j = i; j < L; j++, e++)
+                o[e] += (float)G[(size_t)i * L + j] + (i != j ? (float)G[(size_t)j * L + i] : 0.f);
+          }
+          ip += n_compat_params(m, t);
+        }
+        if (kernel_grad) {
+          const double* G = h.data() + ker_slot[slot];
+          float* o = kernel_grad + ik;
+          const int d = t->d;
+          if (t->ktype == DCRF_DIAG_KERNEL) {
+            for (int j = 0; j < d; j++) o[j] += (float)G[j];
+          } else if (t->ktype == DCRF_FULL_KERNEL) {  // p(r, c) at r + c*d (column-major resize, pairwise.cpp:160)
+            for (int r = 0; r < d; r++)
+              for (int c = 0; c < d; c++) o[r + (size_t)c * d] += (float)G[(size_t)r * d + c];
+          }
+          ik += n_kernel_params(t);
+        }
+      }
+    }
+  });
+}
+
 dcrf_status dcrf_set_iteration_mode(dcrf_t* m, int mode) {
   return guarded([&] {
     DCRF_REQUIRE(m && mode >= 0 && mode <= 2, "bad iteration mode");

@@ -191,6 +191,9 @@ static const int kMaxFeatureDims = 32;
 // index is an extra key coordinate) and come out concatenated with id offsets, identical to separate builds
 void lattice_build(Ctx cx, const FeatureSource& src, int d, int N, Lattice* out, int npi = 0);
 
+// the features of `src` (optionally transformed by kernel parameters, see lattice.cu) as a d x N row-major device array
+void materialize_features(Ctx cx, const FeatureSource& src, int d, int N, int ktype, const float* params, float* out_dxN);
+
 // ---------------------------------------------------------------------------------------------
 // filter / update kernels (filter.cu)
 // ---------------------------------------------------------------------------------------------
@@ -287,6 +290,26 @@ void launch_matrix_compat_tc(Ctx cx, RowLayout rl, int N, const float* Bhi, cons
 // Permutohedral::gradient (permutohedral.cpp:612-695), learn.cu: df (N x d, pixel-major, device) = d/df a^T K b for the
 // pixel-major N x Lp row arrays a and b; A and B are two zeroed (V+1) x Lp scratch buffers
 void lattice_gradient(Ctx cx, const Lattice& lt, RowLayout rl, const float* a, const float* b, float* A, float* B, float* df);
+
+// DenseCRF::gradient building blocks (learn.cu).  G[r*rb + c] (diag: G[r], ra == rb) = sum over the N variables of
+// A[i*sai + r*sar] * B[i*sbi + c*sbr], accumulated in double in a fixed order (G: device doubles)
+void launch_outer_sums(Ctx cx, int N, const float* A, size_t sai, size_t sar, int ra, const float* B, size_t sbi, size_t sbr,
+                       int rb, bool diag, double* G);
+// LogLikelihood / Hamming (objective.cpp:37-50, :67-80): b = d_mul_Q, *value (device) = the objective
+void launch_objective_point(Ctx cx, RowLayout rl, int N, int kind, const int16_t* gt, float robust, const float* cw, const float* Q,
+                            float* b, double* value);
+// IntersectionOverUnion (objective.cpp:83-109): rows whose column sums are in[] and un[] - 1e-20; then d_mul_Q from them
+void launch_iou_rows(Ctx cx, RowLayout rl, int N, const int16_t* gt, const float* Q, float* in_rows, float* un_rows);
+void launch_iou_b(Ctx cx, RowLayout rl, int N, const int16_t* gt, const float* Q, const double* in, const double* un, float* b);
+// sumAndNormalize (densecrf.cpp:107-114) on x = in (mul false) or in .* Q
+void launch_sum_and_normalize(Ctx cx, RowLayout rl, int N, const float* in, const float* Q, bool mul, float* out);
+void launch_scale_rows(Ctx cx, RowLayout rl, int N, const float* x, const float* norm, float* out);   // x * norm.asDiagonal()
+void launch_compat_pointwise(Ctx cx, RowLayout rl, int N, const CompatDev& c, const float* x, float* out);  // Potts / Diagonal apply
+void launch_add_rows(Ctx cx, RowLayout rl, int N, const float* x, float* acc);                          // acc += x
+// the first argument of featureGradient's inner kernelGradient for the three normalised cases (pairwise.cpp:96-97, :105-106, :113-114)
+void launch_feature_gradient_input(Ctx cx, RowLayout rl, int N, int ntype, const float* a, const float* fb, const float* fa,
+                                   const float* b, const float* norm, float* out);
+void launch_neg_add(Ctx cx, size_t n, const float* r, float* kg);  // kg = -r + kg
 
 // layout conversion at the boundary
 // batch > 1: `batch` images, each with its own (L, N) planes and N consecutive rows

@@ -500,6 +500,34 @@ void build_impl(Ctx cx, const ElevateParams& ep, Lattice* L) {
 
 }  // namespace
 
+// f_ of DenseKernel (pairwise.cpp:117) as a d x N row-major device array, whatever the features came from; with
+// `params` (device) the transformed features DenseKernel::setParameters builds the lattice from (:139-151):
+// ktype 1 (DIAG_KERNEL): p[k] * f[k][i]; ktype 2 (FULL_KERNEL): sum_j P(k, j) f[j][i], P column-major, the sum taken in
+// ascending j from zero with every product and sum rounded (the order of Eigen's product kernel over the depth)
+namespace {
+__global__ void k_materialize_features(FeatureSource src, int d, int N, int ktype, const float* __restrict__ params,
+                                       float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  float f[kMaxFeatureDims];
+  for (int k = 0; k < d; k++) f[k] = feature_of(src, k, i, N);
+  for (int k = 0; k < d; k++) {
+    float v = f[k];
+    if (ktype == 1) {
+      v = __fmul_rn(params[k], f[k]);
+    } else if (ktype == 2) {
+      v = 0.f;
+      for (int j = 0; j < d; j++) v = __fadd_rn(v, __fmul_rn(params[k + j * d], f[j]));
+    }
+    out[(size_t)k * N + i] = v;
+  }
+}
+}  // namespace
+void materialize_features(Ctx cx, const FeatureSource& src, int d, int N, int ktype, const float* params, float* out_dxN) {
+  LaunchScope ls(cx.prof, cx.stream, "materialize_features");
+  k_materialize_features<<<(N + kThreads - 1) / kThreads, kThreads, 0, cx.stream>>>(src, d, N, ktype, params, out_dxN);
+}
+
 void Lattice::release(cudaStream_t s) {
   dev_free(pix, s);
   dev_free(csr_start, s);

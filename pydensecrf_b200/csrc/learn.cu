@@ -95,3 +95,273 @@ void lattice_gradient(Ctx cx, const Lattice& lt, RowLayout rl, const float* a, c
 }
 
 }  // namespace dcrf
+
+// ================================================================================================================
+// DenseCRF::gradient (src/densecrf.cpp:237-297): the per-pixel and reduction kernels around the filters.  Everything
+// works on the device row layout (N rows of Lp floats, one row per variable); sums over the variables are accumulated
+// in double through a fixed two-level order (a block per chunk of variables, then the chunks in ascending order), so
+// they are deterministic and at least as accurate as the reference's float Eigen reductions they stand for.
+// ================================================================================================================
+namespace dcrf {
+namespace {
+
+constexpr int kRedThreads = 256;
+constexpr int kOutPerThread = 4;                       // outputs a thread accumulates per pass
+constexpr int kOutPerPass = kRedThreads * kOutPerThread;
+constexpr int kTileBytes = 40 * 1024;                  // shared-memory tile of A and B rows
+
+// part[chunk][o] = sum over the chunk's variables i of A[i*sai + r*sar] * B[i*sbi + c*sbr], o = r*rb + c (diag: r = c = o)
+__global__ void __launch_bounds__(kRedThreads)
+    k_outer_partial(int N, int per_chunk, const float* __restrict__ A, size_t sai, size_t sar, int ra,
+                    const float* __restrict__ B, size_t sbi, size_t sbr, int rb, int diag, int nout, int TP,
+                    double* __restrict__ part) {
+  extern __shared__ float sh[];
+  float* As = sh;                      // TP x ra
+  float* Bs = sh + (size_t)TP * ra;    // TP x rb
+  const int chunk = blockIdx.x, pass = blockIdx.y;
+  const int i0 = chunk * per_chunk, i1 = min(N, i0 + per_chunk);
+  int r[kOutPerThread], c[kOutPerThread];
+  double acc[kOutPerThread];
+  for (int j = 0; j < kOutPerThread; j++) {
+    const int o = pass * kOutPerPass + j * kRedThreads + threadIdx.x;
+    acc[j] = 0.0;
+    if (o < nout) {
+      r[j] = diag ? o : o / rb;
+      c[j] = diag ? o : o % rb;
+    } else {
+      r[j] = -1, c[j] = 0;
+    }
+  }
+  for (int t0 = i0; t0 < i1; t0 += TP) {
+    const int tp = min(TP, i1 - t0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < tp * ra; e += kRedThreads) As[e] = A[(size_t)(t0 + e / ra) * sai + (size_t)(e % ra) * sar];
+    for (int e = threadIdx.x; e < tp * rb; e += kRedThreads) Bs[e] = B[(size_t)(t0 + e / rb) * sbi + (size_t)(e % rb) * sbr];
+    __syncthreads();
+    for (int j = 0; j < kOutPerThread; j++) {
+      if (r[j] < 0) continue;
+      double a = acc[j];
+      for (int p = 0; p < tp; p++) a += (double)As[p * ra + r[j]] * (double)Bs[p * rb + c[j]];
+      acc[j] = a;
+    }
+  }
+  for (int j = 0; j < kOutPerThread; j++) {
+    const int o = pass * kOutPerPass + j * kRedThreads + threadIdx.x;
+    if (o < nout) part[(size_t)chunk * nout + o] = acc[j];
+  }
+}
+__global__ void k_outer_final(int nchunks, int nout, const double* __restrict__ part, double* __restrict__ G) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= nout) return;
+  double s = 0.0;
+  for (int ch = 0; ch < nchunks; ch++) s += part[(size_t)ch * nout + o];
+  G[o] = s;
+}
+
+// one thread per variable ------------------------------------------------------------------------------------------
+// LogLikelihood::evaluate (objective.cpp:37-50) and Hamming::evaluate (:67-80): b = d_mul_Q, term[i] = the variable's
+// addend of the objective value (double)
+__global__ void k_objective_point(int N, int L, int Lp, int kind, const int16_t* __restrict__ gt, float robust,
+                                  const float* __restrict__ cw, const float* __restrict__ Q, float* __restrict__ b,
+                                  double* __restrict__ term) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  float* bi = b + (size_t)i * Lp;
+  for (int l = 0; l < Lp; l++) bi[l] = 0.f;
+  const int g = gt[i];
+  double t = 0.0;
+  if (g >= 0 && g < L) {
+    const float q = Q[(size_t)i * Lp + g];
+    if (kind == DCRF_OBJECTIVE_LOGLIKELIHOOD) {
+      const float qq = fmaxf(__fadd_rn(q, robust), 1e-20f);
+      t = log((double)qq) / N;
+      bi[g] = __fdiv_rn(__fdiv_rn(q, qq), (float)N);
+    } else {
+      const float qq = __fmul_rn(cw[g], q);
+      t = (double)qq;
+      bi[g] = qq;
+    }
+  }
+  term[i] = t;
+}
+// IntersectionOverUnion::evaluate (:83-109), first loop: rows whose column sums are in[] and un[] - 1e-20
+__global__ void k_iou_rows(int N, int L, int Lp, const int16_t* __restrict__ gt, const float* __restrict__ Q,
+                           float* __restrict__ in_rows, float* __restrict__ un_rows) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const int g = gt[i];
+  const bool ok = g >= 0 && g < L;
+  for (int l = 0; l < Lp; l++) {
+    const float q = l < L ? Q[(size_t)i * Lp + l] : 0.f;
+    in_rows[(size_t)i * Lp + l] = (ok && l == g) ? q : 0.f;
+    un_rows[(size_t)i * Lp + l] = !ok || l >= L ? 0.f : (l == g ? 1.f : q);
+  }
+}
+// second loop: d_mul_Q from the class sums (double arithmetic, as the reference's VectorXd in / un make it)
+__global__ void k_iou_b(int N, int L, int Lp, const int16_t* __restrict__ gt, const float* __restrict__ Q,
+                        const double* __restrict__ in, const double* __restrict__ un, float* __restrict__ b) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const int g = gt[i];
+  const bool ok = g >= 0 && g < L;
+  for (int l = 0; l < Lp; l++) {
+    float v = 0.f;
+    if (ok && l < L) {
+      const double q = (double)Q[(size_t)i * Lp + l];
+      const double u = un[l] + 1e-20;
+      v = l == g ? (float)(q / (u * L)) : (float)(-q * in[l] / (u * u * L));
+    }
+    b[(size_t)i * Lp + l] = v;
+  }
+}
+// sumAndNormalize (densecrf.cpp:107-114): out = sum(x) * q - x per variable, x = in (mul == 0) or in .* Q (:290)
+__global__ void k_sum_and_normalize(int N, int L, int Lp, const float* __restrict__ in, const float* __restrict__ Q, int mul,
+                                    float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const float* x = in + (size_t)i * Lp;
+  const float* q = Q + (size_t)i * Lp;
+  float s = 0.f;
+  for (int l = 0; l < L; l++) s = __fadd_rn(s, mul ? __fmul_rn(x[l], q[l]) : x[l]);
+  float* o = out + (size_t)i * Lp;
+  for (int l = 0; l < Lp; l++) {
+    const float xl = l < L ? (mul ? __fmul_rn(x[l], q[l]) : x[l]) : 0.f;
+    o[l] = l < L ? __fsub_rn(__fmul_rn(s, q[l]), xl) : 0.f;
+  }
+}
+
+// one thread per element -------------------------------------------------------------------------------------------
+enum { EW_SCALE_ROWS = 0, EW_POTTS = 1, EW_DIAG = 2, EW_ADD = 3, EW_SYM = 4, EW_PROD_NORM2 = 5 };
+// EW_SCALE_ROWS: out = x * norm[i]            (a * norm_.asDiagonal(), pairwise.cpp:92)
+// EW_POTTS:      out = s * x                  (-w_ * Q, labelcompatibility.cpp:47)
+// EW_DIAG:       out = vec[l] * x             (w_.asDiagonal() * Q, :67)
+// EW_ADD:        out = out + x                (tmp1 += tmp2, densecrf.cpp:288)
+// EW_SYM:        out = 0.5 * (x*y + z*w) * norm^3   (pairwise.cpp:96-97)
+// EW_PROD_NORM2: out = (x*y) * norm^2               (:105-106, :113-114)
+__global__ void k_elementwise(int op, size_t n, int Lp, const float* __restrict__ x, const float* __restrict__ y,
+                              const float* __restrict__ z, const float* __restrict__ w, const float* __restrict__ vec,
+                              float s, float* __restrict__ out) {
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const size_t i = e / Lp;
+  const int l = (int)(e % Lp);
+  float r;
+  switch (op) {
+    case EW_SCALE_ROWS: r = __fmul_rn(x[e], vec[i]); break;
+    case EW_POTTS: r = __fmul_rn(s, x[e]); break;
+    case EW_DIAG: r = __fmul_rn(vec[l], x[e]); break;
+    case EW_ADD: r = __fadd_rn(out[e], x[e]); break;
+    case EW_SYM: {
+      const float nn = vec[i], n3 = __fmul_rn(__fmul_rn(nn, nn), nn);
+      r = __fmul_rn(__fmul_rn(0.5f, __fadd_rn(__fmul_rn(x[e], y[e]), __fmul_rn(z[e], w[e]))), n3);
+      break;
+    }
+    default: {
+      const float nn = vec[i];
+      r = __fmul_rn(__fmul_rn(x[e], y[e]), __fmul_rn(nn, nn));
+    }
+  }
+  out[e] = r;
+}
+// featureGradient's last line: fg = -r + kg (pairwise.cpp:98, :107, :115), in place on kg
+__global__ void k_neg_add(size_t n, const float* __restrict__ r, float* __restrict__ kg) {
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < n) kg[e] = __fadd_rn(-r[e], kg[e]);
+}
+__global__ void k_sum_doubles(int n, const double* __restrict__ x, int per, double* __restrict__ part) {
+  // fixed order: thread t adds its contiguous slice, the slices are added in ascending order by k_outer_final
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i0 = t * per;
+  double s = 0.0;
+  for (int i = i0; i < min(n, i0 + per); i++) s += x[i];
+  part[t] = s;
+}
+
+inline int blocks_for(size_t n, int threads) { return (int)((n + threads - 1) / threads); }
+
+}  // namespace
+
+void launch_outer_sums(Ctx cx, int N, const float* A, size_t sai, size_t sar, int ra, const float* B, size_t sbi, size_t sbr,
+                       int rb, bool diag, double* G) {
+  DCRF_REQUIRE(ra >= 1 && rb >= 1 && (size_t)(ra + rb) * sizeof(float) <= kTileBytes, "too many rows for the reduction kernel");
+  const int nout = diag ? ra : ra * rb;
+  const int TP = std::max(1, std::min(64, (int)(kTileBytes / ((size_t)(ra + rb) * sizeof(float)))));
+  int nchunks = std::max(1, std::min(592, (N + 4 * TP - 1) / (4 * TP)));
+  const int per_chunk = (N + nchunks - 1) / nchunks;
+  nchunks = (N + per_chunk - 1) / per_chunk;
+  double* part = dev_alloc<double>((size_t)nchunks * nout, cx.stream);
+  {
+    LaunchScope ls(cx.prof, cx.stream, "grad_outer_sums");
+    dim3 grid(nchunks, (nout + kOutPerPass - 1) / kOutPerPass);
+    k_outer_partial<<<grid, kRedThreads, (size_t)TP * (ra + rb) * sizeof(float), cx.stream>>>(N, per_chunk, A, sai, sar, ra, B, sbi,
+                                                                                              sbr, rb, diag ? 1 : 0, nout, TP, part);
+  }
+  {
+    LaunchScope ls(cx.prof, cx.stream, "grad_outer_final");
+    k_outer_final<<<blocks_for(nout, 128), 128, 0, cx.stream>>>(nchunks, nout, part, G);
+  }
+  dev_free(part, cx.stream);
+}
+
+void launch_objective_point(Ctx cx, RowLayout rl, int N, int kind, const int16_t* gt, float robust, const float* cw, const float* Q,
+                            float* b, double* value) {
+  double* term = dev_alloc<double>(N, cx.stream);
+  {
+    LaunchScope ls(cx.prof, cx.stream, "grad_objective");
+    k_objective_point<<<blocks_for(N, 128), 128, 0, cx.stream>>>(N, rl.L, rl.Lp, kind, gt, robust, cw, Q, b, term);
+  }
+  const int per = 256, nt = (N + per - 1) / per;
+  double* part = dev_alloc<double>(nt, cx.stream);
+  {
+    LaunchScope ls(cx.prof, cx.stream, "grad_objective_sum");
+    k_sum_doubles<<<blocks_for(nt, 128), 128, 0, cx.stream>>>(N, term, per, part);
+    k_outer_final<<<1, 32, 0, cx.stream>>>(nt, 1, part, value);
+  }
+  dev_free(term, cx.stream);
+  dev_free(part, cx.stream);
+}
+void launch_iou_rows(Ctx cx, RowLayout rl, int N, const int16_t* gt, const float* Q, float* in_rows, float* un_rows) {
+  LaunchScope ls(cx.prof, cx.stream, "grad_objective");
+  k_iou_rows<<<blocks_for(N, 128), 128, 0, cx.stream>>>(N, rl.L, rl.Lp, gt, Q, in_rows, un_rows);
+}
+void launch_iou_b(Ctx cx, RowLayout rl, int N, const int16_t* gt, const float* Q, const double* in, const double* un, float* b) {
+  LaunchScope ls(cx.prof, cx.stream, "grad_objective");
+  k_iou_b<<<blocks_for(N, 128), 128, 0, cx.stream>>>(N, rl.L, rl.Lp, gt, Q, in, un, b);
+}
+void launch_sum_and_normalize(Ctx cx, RowLayout rl, int N, const float* in, const float* Q, bool mul, float* out) {
+  LaunchScope ls(cx.prof, cx.stream, "grad_sum_normalize");
+  k_sum_and_normalize<<<blocks_for(N, 128), 128, 0, cx.stream>>>(N, rl.L, rl.Lp, in, Q, mul ? 1 : 0, out);
+}
+static void elementwise(Ctx cx, int op, size_t n, int Lp, const float* x, const float* y, const float* z, const float* w,
+                        const float* vec, float s, float* out) {
+  LaunchScope ls(cx.prof, cx.stream, "grad_elementwise");
+  k_elementwise<<<blocks_for(n, 256), 256, 0, cx.stream>>>(op, n, Lp, x, y, z, w, vec, s, out);
+}
+void launch_scale_rows(Ctx cx, RowLayout rl, int N, const float* x, const float* norm, float* out) {
+  elementwise(cx, EW_SCALE_ROWS, (size_t)N * rl.Lp, rl.Lp, x, nullptr, nullptr, nullptr, norm, 0.f, out);
+}
+void launch_compat_pointwise(Ctx cx, RowLayout rl, int N, const CompatDev& c, const float* x, float* out) {
+  if (c.kind == DCRF_COMPAT_POTTS)
+    elementwise(cx, EW_POTTS, (size_t)N * rl.Lp, rl.Lp, x, nullptr, nullptr, nullptr, nullptr, c.neg_w, out);
+  else
+    elementwise(cx, EW_DIAG, (size_t)N * rl.Lp, rl.Lp, x, nullptr, nullptr, nullptr, c.diag, 0.f, out);
+}
+void launch_add_rows(Ctx cx, RowLayout rl, int N, const float* x, float* acc) {
+  elementwise(cx, EW_ADD, (size_t)N * rl.Lp, rl.Lp, x, nullptr, nullptr, nullptr, nullptr, 0.f, acc);
+}
+void launch_feature_gradient_input(Ctx cx, RowLayout rl, int N, int ntype, const float* a, const float* fb, const float* fa,
+                                   const float* b, const float* norm, float* out) {
+  const size_t n = (size_t)N * rl.Lp;
+  if (ntype == DCRF_NORMALIZE_SYMMETRIC)
+    elementwise(cx, EW_SYM, n, rl.Lp, a, fb, fa, b, norm, 0.f, out);
+  else if (ntype == DCRF_NORMALIZE_AFTER)
+    elementwise(cx, EW_PROD_NORM2, n, rl.Lp, a, fb, nullptr, nullptr, norm, 0.f, out);
+  else
+    elementwise(cx, EW_PROD_NORM2, n, rl.Lp, fa, b, nullptr, nullptr, norm, 0.f, out);
+}
+void launch_neg_add(Ctx cx, size_t n, const float* r, float* kg) {
+  LaunchScope ls(cx.prof, cx.stream, "grad_elementwise");
+  k_neg_add<<<blocks_for(n, 256), 256, 0, cx.stream>>>(n, r, kg);
+}
+
+}  // namespace dcrf

@@ -235,6 +235,36 @@ def utils_golden():
     save("utils.npz", **out)
 
 
+def gradient_model():
+    """DenseCRF::gradient and the parameter vectors of the unmodified reference on tests/gradient_cases.py, before and
+    after an update of all three parameter groups (learning path)."""
+    from tests import gradient_cases as gc
+    from tests.test_gradient import KIND, updated_parameters
+    out = {}
+    for case in gc.CASES:
+        c = gc.make(case)
+        n = c["name"]
+        ref = gc.build(po.CRF(c["N"], c["L"], "ref"), c)
+        ob = c["objective"]
+        kind = KIND[ob[0]]
+        robust = ob[1] if kind == 0 else 0.0
+        cw = po.hamming_weights(c["gt"], ob[1], c["L"]) if kind == 1 else np.zeros(0, np.float32)
+        out[n + "/class_weight"] = cw
+        for g in range(3):
+            out[n + "/params%d" % g] = ref.parameters(g)
+        r = ref.gradient(c["n_iter"], kind, c["gt"], robust, cw)
+        out[n + "/value"], out[n + "/unary"], out[n + "/lbl"], out[n + "/kernel"] = np.float64(r[0]), r[1], r[2], r[3]
+        new = updated_parameters(c, ref.parameters(1), ref.parameters(0))
+        for g in range(3):
+            out[n + "/new%d" % g] = new[g]
+            if new[g].size:
+                ref.setParameters(g, new[g])
+        r = ref.gradient(c["n_iter"], kind, c["gt"], robust, cw)
+        out[n + "/value2"], out[n + "/unary2"], out[n + "/lbl2"], out[n + "/kernel2"] = np.float64(r[0]), r[1], r[2], r[3]
+        out[n + "/Q2"] = np.ascontiguousarray(ref.inference(c["n_iter"]))
+    save("gradient_model.npz", **out)
+
+
 if __name__ == "__main__":
     po.build()
     assert po.available("ref"), "oracle/_ref/libref.so missing: /root/reference not visible?"
@@ -246,3 +276,4 @@ if __name__ == "__main__":
     mid()
     utils_golden()
     gradient()
+    gradient_model()
