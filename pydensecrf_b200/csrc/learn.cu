@@ -268,9 +268,10 @@ __global__ void k_neg_add(size_t n, const float* __restrict__ r, float* __restri
   const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e < n) kg[e] = __fadd_rn(-r[e], kg[e]);
 }
-__global__ void k_sum_doubles(int n, const double* __restrict__ x, int per, double* __restrict__ part) {
+__global__ void k_sum_doubles(int n, const double* __restrict__ x, int per, int nparts, double* __restrict__ part) {
   // fixed order: thread t adds its contiguous slice, the slices are added in ascending order by k_outer_final
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nparts) return;
   const int i0 = t * per;
   double s = 0.0;
   for (int i = i0; i < min(n, i0 + per); i++) s += x[i];
@@ -314,7 +315,7 @@ void launch_objective_point(Ctx cx, RowLayout rl, int N, int kind, const int16_t
   double* part = dev_alloc<double>(nt, cx.stream);
   {
     LaunchScope ls(cx.prof, cx.stream, "grad_objective_sum");
-    k_sum_doubles<<<blocks_for(nt, 128), 128, 0, cx.stream>>>(N, term, per, part);
+    k_sum_doubles<<<blocks_for(nt, 128), 128, 0, cx.stream>>>(N, term, per, nt, part);
     k_outer_final<<<1, 32, 0, cx.stream>>>(nt, 1, part, value);
   }
   dev_free(term, cx.stream);
