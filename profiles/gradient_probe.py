@@ -25,8 +25,11 @@ R = 5
 for _ in range(R):
     got = m.gradient(IT, obj)
 t_gpu = (time.perf_counter() - t0) / R
-t0 = time.perf_counter()
-m.inference(IT); np.asarray(m.inference(IT))[0, 0]
+m._profile_enable(True)
+m.gradient(IT, obj)
+prof = sorted(((k, v[0], v[1]) for k, v in m._profile_read().items()), key=lambda e: -e[2])
+m._profile_enable(False)
+print("per kernel class (name, launches, ms):", ", ".join("%s %d %.3f" % e for e in prof), flush=True)
 print("engine: gradient(%d) %.2f ms at %dx%dx%d" % (IT, t_gpu * 1e3, W, H, L), flush=True)
 
 r = po.CRF((W, H), L, "ref")

@@ -25,6 +25,7 @@ struct GradParams {
   float scale[kMaxFeatureDims];   // scale_factor (:624-626)
 };
 
+template <bool VEC4>
 __global__ void __launch_bounds__(kThreads)
     k_lattice_grad(GradParams p, const PixEntry* __restrict__ pix, const uint8_t* __restrict__ rank,
                    const float* __restrict__ val, const float* __restrict__ other, float* __restrict__ df) {
@@ -50,6 +51,35 @@ __global__ void __launch_bounds__(kThreads)
   }
   float g[kMaxFeatureDims];
   for (int j = 0; j < d; j++) g[j] = 0.f;
+  if (VEC4) {
+    // four labels per row access (rows are whole float4 chunks for L >= 3); every label still runs the same operations
+    // in the same order, and a gradient entry still accumulates over the labels in ascending order
+    for (int k4 = 0; k4 < p.Lp; k4 += 4) {
+      const float4 ok4 = *reinterpret_cast<const float4*>(other + (size_t)i * p.Lp + k4);
+      const float okc[4] = {ok4.x, ok4.y, ok4.z, ok4.w};
+      float sm[4];
+      {
+        const float4 a = *reinterpret_cast<const float4*>(val + (size_t)o0[0] * p.Lp + k4);
+        const float4 b = *reinterpret_cast<const float4*>(val + (size_t)o1[0] * p.Lp + k4);
+        const float ac[4] = {a.x, a.y, a.z, a.w}, bc[4] = {b.x, b.y, b.z, b.w};
+        for (int c = 0; c < 4; c++) sm[c] = __fsub_rn(__fadd_rn(0.f, __fmul_rn(p.alpha, ac[c])), __fmul_rn(p.alpha, bc[c]));
+      }
+      for (int j = 1; j <= d; j++) {
+        const float4 a = *reinterpret_cast<const float4*>(val + (size_t)o0[j] * p.Lp + k4);
+        const float4 b = *reinterpret_cast<const float4*>(val + (size_t)o1[j] * p.Lp + k4);
+        const float ac[4] = {a.x, a.y, a.z, a.w}, bc[4] = {b.x, b.y, b.z, b.w};
+        float gj = g[j - 1];
+        for (int c = 0; c < 4; c++) {
+          if (k4 + c >= p.L) break;
+          const float ra = __fsub_rn(__fadd_rn(0.f, __fmul_rn(p.alpha, ac[c])), __fmul_rn(p.alpha, bc[c]));
+          const float v = __fmul_rn(p.scale[j - 1], __fsub_rn(sm[c], __fmul_rn((float)j, ra)));
+          gj = __fadd_rn(gj, __fmul_rn(okc[c], v));
+          sm[c] = __fadd_rn(sm[c], ra);
+        }
+        g[j - 1] = gj;
+      }
+    }
+  } else
   for (int k = 0; k < p.L; k++) {
     const float ok = other[(size_t)i * p.Lp + k];
     // r_a[0][k], then sm = r_a[0][k]; for j >= 1: v = scale[j-1] * (sm - j * r_a[j][k]); grad_j += other * v; sm += r_a[j][k]
@@ -90,7 +120,10 @@ void lattice_gradient(Ctx cx, const Lattice& lt, RowLayout rl, const float* a, c
       std::swap(src, dst);
     }
     LaunchScope ls(cx.prof, cx.stream, "lattice_grad");
-    k_lattice_grad<<<(lt.N + kThreads - 1) / kThreads, kThreads, 0, cx.stream>>>(p, lt.pix, lt.rank, src, dir ? a : b, df);
+    if (rl.vec == 4)
+      k_lattice_grad<true><<<(lt.N + kThreads - 1) / kThreads, kThreads, 0, cx.stream>>>(p, lt.pix, lt.rank, src, dir ? a : b, df);
+    else
+      k_lattice_grad<false><<<(lt.N + kThreads - 1) / kThreads, kThreads, 0, cx.stream>>>(p, lt.pix, lt.rank, src, dir ? a : b, df);
   }
 }
 
