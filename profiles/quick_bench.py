@@ -39,6 +39,8 @@ for mask in masks:
     if ref is None:
         ref = q
     same = bool(np.array_equal(q, ref))
+    if not same:
+        print("    max |dQ| against the first mask: %.3g" % float(np.abs(q - ref).max()))
     import hashlib
     print("%-28s q=%s mask=%d  %.3f ms  same_bits=%s  %s" % (
         tag, hashlib.sha1(q.tobytes()).hexdigest()[:8], mask, ms, same,

@@ -341,6 +341,7 @@ struct Term {
   float *valA = nullptr, *valB = nullptr;  // (V+1) x Lp ping-pong value buffers (one allocation)
   float* msg = nullptr;                    // N x Lp message of this term (tensor-core update path only)
   float* qn = nullptr;                     // N x Lp: Q * diag(norm), written by the update kernel for this term's next splat
+  CsrEntry* csr_baked = nullptr;           // the lattice's contribution list with w * norm[pix] as weights (VAR_BAKED_NORM)
   size_t val_bytes = 0;
   // learning path (DenseKernel's f_, ktype_, parameters_; pairwise.cpp:35-39): where the features came from, kept for
   // DIAG_KERNEL / FULL_KERNEL terms so that kernelParameters / kernelGradient can form f_ when they are first asked for
@@ -407,11 +408,15 @@ namespace {
 // Kernel variants (bit mask; every combination gives identical bits).  1: wide-lane update kernel (filter_wide.cu);
 // 2: the update kernel also writes Q * diag(norm_k) for every pre-normalised term and the next splat reads that copy
 // instead of Q and norm.  $DCRF_B200_VARIANT / dcrf_set_kernel_variant choose for A/B timing and tests.
-enum { VAR_WIDE_UPDATE = 1, VAR_PRESCALED_Q = 2, VAR_ALL = 3 };
+// 4: the pre-normalisation of a term is folded into its contribution weights, (w * norm_i) * Q_i instead of the
+// reference's w * (norm_i * Q_i) (pairwise.cpp:65-66 then permutohedral.cpp:553): one extra rounding per contribution
+// (~1e-7 on Q), for which the update kernel writes ONE Q that every splat reads instead of a pre-scaled copy per term.
+// Overrides 2.  NOT bit-identical to the other variants.
+enum { VAR_WIDE_UPDATE = 1, VAR_PRESCALED_Q = 2, VAR_BAKED_NORM = 4, VAR_ALL = 7, VAR_DEFAULT = 3 };
 int default_variant() {
   static const int v = [] {
     const char* e = std::getenv("DCRF_B200_VARIANT");
-    return e ? (std::atoi(e) & VAR_ALL) : VAR_ALL;
+    return e ? (std::atoi(e) & VAR_ALL) : VAR_DEFAULT;
   }();
   return v;
 }
@@ -469,7 +474,7 @@ void term_free(dcrf_model* m, Term* t) {
   cudaStream_t s = m->stream;
   if (!t->shared) t->lat.release(s);
   for (void* p : {(void*)t->norm, (void*)t->diag, (void*)t->Wm, (void*)t->Whi, (void*)t->Wlo, (void*)t->valA, (void*)t->msg, (void*)t->qn,
-                  t->src_buf, (void*)t->feat0})
+                  t->src_buf, (void*)t->feat0, (void*)t->csr_baked})
     dev_free(p, s);
   delete t;
 }
@@ -637,6 +642,11 @@ void filter_all_terms(dcrf_model* m, const float* Q, const float** vals, bool sl
     }
     // prescaled: the previous update kernel left Q * diag(norm) in t->qn (bit-identical to scaling in the splat)
     const bool pre_done = prescaled && t->pre() && t->qn;
+    if ((m->variant & VAR_BAKED_NORM) && t->pre() && t->csr_baked) {
+      Lattice lb = t->lat;  // shallow: the same lattice with the norm-carrying contribution list
+      lb.csr = t->csr_baked;
+      vals[k] = run_filter(ck, lb, m->rl, Q, nullptr, t->valA, t->valB);
+    } else
     vals[k] = run_filter(ck, t->lat, m->rl, pre_done ? t->qn : Q, (t->pre() && !pre_done) ? t->norm : nullptr, t->valA, t->valB);
     if (slice_msgs) {
       ensure_msg(m, t);
@@ -661,10 +671,18 @@ bool can_tc_update(dcrf_model* m) {
 bool fuse_wanted(dcrf_model* m) { return m->iter_mode == 2 || (m->iter_mode == 0 && can_fuse(m)); }
 // inference(n) with the fused kernel and at least one pre-normalised term: the iterations hand Q * diag(norm) on
 bool prescale_wanted(dcrf_model* m) {
-  if (!(m->variant & VAR_PRESCALED_Q) || !fuse_wanted(m) || !can_fuse(m)) return false;
+  if (!(m->variant & VAR_PRESCALED_Q) || (m->variant & VAR_BAKED_NORM) || !fuse_wanted(m) || !can_fuse(m)) return false;
   for (Term* t : m->terms)
     if (t->pre()) return true;
   return false;
+}
+void ensure_baked(dcrf_model* m) {
+  if (!(m->variant & VAR_BAKED_NORM)) return;
+  for (Term* t : m->terms)
+    if (t->pre() && !t->csr_baked && t->lat.E > 0) {
+      t->csr_baked = dev_alloc<CsrEntry>((size_t)t->lat.E, m->stream);
+      launch_bake_csr(m->cx(), (size_t)t->lat.E, t->lat.csr, t->norm, t->csr_baked);
+    }
 }
 void ensure_qn(dcrf_model* m) {
   for (Term* t : m->terms)
@@ -1449,6 +1467,7 @@ dcrf_status dcrf_inference_into(dcrf_t* m, int n_iterations, dcrf_mat_t* Q) {
     for (Term* t : m->terms) ensure_val(m, t);
     ensure_scratch_if_staged(m);
     if (n_iterations > 0 && prescale_wanted(m)) ensure_qn(m);
+    ensure_baked(m);
     ensure_aux(m, (int)m->terms.size());
     if (m->use_graphs && !m->prof.enabled && n_iterations > 0) {
       dcrf_model::GraphEntry* hit = nullptr;
@@ -1541,6 +1560,7 @@ dcrf_status dcrf_step_inference(dcrf_t* m, dcrf_mat_t* Q, dcrf_mat_t* tmp1, dcrf
     DCRF_REQUIRE(m && Q, "null argument");
     DeviceGuard g(m->device);
     float* q = mat_device(m, Q, true);
+    ensure_baked(m);
     mf_step(m, q, false);
     DCRF_CUDA(cudaGetLastError());
     mat_written(m, Q);
@@ -1886,6 +1906,7 @@ struct BatchChunk {
     for (Term* t : m->terms) ensure_val(m, t);
     ensure_scratch_if_staged(m);
     if (p.n_iterations > 0 && prescale_wanted(m)) ensure_qn(m);
+    ensure_baked(m);
     ensure_aux(m, (int)m->terms.size());
     mf_run(m, q, p.n_iterations);
     int16_t* dl = dev_alloc<int16_t>(N, s);
@@ -2296,7 +2317,8 @@ void term_set_kernel_params(dcrf_model* m, Term* t, const float* v) {
   t->lat = Lattice();
   dev_free(t->norm, s);
   dev_free(t->valA, s);
-  t->norm = nullptr, t->valA = t->valB = nullptr, t->val_bytes = 0;
+  dev_free(t->csr_baked, s);
+  t->norm = nullptr, t->valA = t->valB = nullptr, t->val_bytes = 0, t->csr_baked = nullptr;
   g.feat = tf;
   try {
     term_init_lattice(m, t, g, d);
@@ -2472,6 +2494,7 @@ dcrf_status dcrf_gradient(dcrf_t* m, int n_iterations, const dcrf_objective* obj
     ensure_scratch_if_staged(m);
     ensure_aux(m, nt);
     std::vector<float*> Q(n_iterations + 1);
+    ensure_baked(m);
     Q[0] = rows();
     mf_init(m, Q[0]);
     for (int it = 0; it < n_iterations; it++) {

@@ -320,6 +320,8 @@ void launch_softmax_planes_to_unary(Ctx cx, RowLayout rl, int N, const float* pl
 void launch_unpack_rows(Ctx cx, RowLayout rl, int N, const float* packed_NxL, float* rows_NxLp);
 void launch_pack_rows(Ctx cx, RowLayout rl, int N, const float* rows_NxLp, float* packed_NxL);
 void launch_fill(Ctx cx, float* p, size_t n, float v);
+// out[e] = {csr[e].pix, csr[e].w * norm[csr[e].pix]}
+void launch_bake_csr(Ctx cx, size_t E, const CsrEntry* csr, const float* norm, CsrEntry* out);
 // norm_raw -> 1/sqrt(x+1e-20) (symmetric) or 1/(x+1e-20), evaluated in double (pairwise.cpp:52-61)
 void launch_norm_transform(Ctx cx, int N, float* norm, bool symmetric);
 // U = Lmat * f for the logistic unary (unary.cpp:50-52); rows_NxLp out

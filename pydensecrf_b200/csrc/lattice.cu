@@ -528,6 +528,21 @@ void materialize_features(Ctx cx, const FeatureSource& src, int d, int N, int kt
   k_materialize_features<<<(N + kThreads - 1) / kThreads, kThreads, 0, cx.stream>>>(src, d, N, ktype, params, out_dxN);
 }
 
+// contribution weights with a term's pre-normalisation folded in: w * norm[pix] (VAR_BAKED_NORM in api.cu)
+namespace {
+__global__ void k_bake_csr(size_t E, const CsrEntry* __restrict__ csr, const float* __restrict__ norm, CsrEntry* __restrict__ out) {
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  CsrEntry c = csr[e];
+  c.w = __fmul_rn(c.w, __ldg(norm + c.pix));
+  out[e] = c;
+}
+}  // namespace
+void launch_bake_csr(Ctx cx, size_t E, const CsrEntry* csr, const float* norm, CsrEntry* out) {
+  LaunchScope ls(cx.prof, cx.stream, "bake_csr");
+  k_bake_csr<<<blocks_for(E), kThreads, 0, cx.stream>>>(E, csr, norm, out);
+}
+
 void Lattice::release(cudaStream_t s) {
   dev_free(pix, s);
   dev_free(csr_start, s);
