@@ -243,7 +243,7 @@ def run_configs(args, dcrf, eigen, world, rank, local, dist, torch, hbm_peak, cp
     """cfg 4 at every N (sharded over the ranks, no collective); cfg 3 / cfg 5 / the noise image at N = 1 only."""
     import bench_configs as bc
 
-    want = set(args.configs.split(",")) if args.configs != "all" else {"cfg2_noise", "cfg3", "cfg4", "cfg5"}
+    want = set(args.configs.split(",")) if args.configs != "all" else {"cfg2_noise", "cfg3", "cfg4", "cfg5", "learning"}
     res = {}
     if "cfg4" in want:
         try:
@@ -257,7 +257,7 @@ def run_configs(args, dcrf, eigen, world, rank, local, dist, torch, hbm_peak, cp
         except Exception as e:  # noqa: BLE001
             res["cfg4"] = {"error": "%s: %s" % (type(e).__name__, e)}
     if world == 1:
-        for name in ("cfg2_noise", "cfg5", "cfg3"):
+        for name in ("cfg2_noise", "cfg5", "learning", "cfg3"):
             if name not in want:
                 continue
             try:
@@ -602,7 +602,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pipelined", action="store_true", help="skip the multi-threaded end-to-end variant")
     ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE configs (cfg 3, 4, 5, noise image)")
-    ap.add_argument("--configs", default="all", help="comma list out of cfg2_noise,cfg3,cfg4,cfg5 (default: all)")
+    ap.add_argument("--configs", default="all", help="comma list out of cfg2_noise,cfg3,cfg4,cfg5,learning (default: all)")
     ap.add_argument("--dist-selftest", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.dist_selftest:

@@ -5,6 +5,7 @@
   cfg4        batch of 1024 512x512 images, 21 labels, 5 iterations, through map_batch_2d; under torchrun the batch is
               sharded over the ranks (one process per GPU, no collective)
   cfg5        generic DenseCRF, 256^3 volume, 2 labels, 4-D bilateral features, FULL_KERNEL, 5 iterations
+  learning    (SURVEY 8f-4, not a BASELINE config) DenseCRF::gradient(5) with all gradients at 512x512, 21 labels
 
 Each entry carries the lattice sizes V, the device time, the stage-model HBM fraction (SURVEY 8d bytes over the measured
 copy bandwidth) and, unless --no-cpu-baseline, a `parity` block against the reference C++ (oracle/_ref, else the C
@@ -140,6 +141,45 @@ def cfg5(dcrf, eigen, device, hbm_peak, cpu):
         t = time.perf_counter() - t0
         out["parity"] = _parity(np.asarray(d.inference(n)), Qc, {"against": which, "iterations": n})
         out["cpu_baseline"] = {"value": D ** 3 * n / t / 1e6, "unit": "MVox*iter/s", "cores": 1, "kind": "reference" if which == "ref" else "port"}
+    return out
+
+
+def learning(dcrf, eigen, device, hbm_peak, cpu):
+    """SURVEY 8f-4 (not a BASELINE config): DenseCRF::gradient with all three gradients at a training-image size."""
+    W, H, L, n = 512, 512, 21, 5
+    img, U = wl.smooth_image(H, W, seed=1, grid=16), wl.softmax_unary(H, W, L, seed=1, grid=8)
+    gt = np.argmax(-U, axis=0).astype(np.int16)
+    gt[::7] = -1
+    d = dcrf.DenseCRF2D(W, H, L, device=device)
+    d.setUnaryEnergy(U)
+    d.addPairwiseGaussian(sxy=3, compat=3)
+    d.addPairwiseBilateral(sxy=80, srgb=13, rgbim=img, compat=10)
+    obj = dcrf.LogLikelihood(gt)
+    got = d.gradient(n, obj)
+    reps = 5
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        got = d.gradient(n, obj)
+    ms = (time.perf_counter() - t0) / reps * 1e3
+    out = {"workload": "DenseCRF2D 512x512, 21 labels, Gaussian(3)+bilateral(80,13) Potts, DIAG kernels: gradient(5) of the "
+                       "LogLikelihood objective, label-compatibility (2) and kernel (2 + 5) gradients",
+           "ms_per_gradient": ms, "timing": "host clock around the blocking call (results come back to the host)",
+           "value": W * H * n / ms / 1e3, "unit": "MPix*iter/s"}
+    po, which = _checker()
+    if cpu and which == "ref":
+        c = po.CRF((W, H), L, "ref")
+        c.setUnaryEnergy(U)
+        c.addPairwiseGaussian(3, 3.0)
+        c.addPairwiseBilateral(80, 13, img, 10.0)
+        t0 = time.perf_counter()
+        want = c.gradient(n, po.LOGLIKELIHOOD, gt)
+        t = time.perf_counter() - t0
+        rel = [float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)) for a, b in zip(got[1:], want[1:]) if b.size]
+        out["parity"] = {"against": "ref", "objective_rel": abs(got[0] - want[0]) / abs(want[0]),
+                         "gradient_max_rel_to_largest_entry": max(rel), "tolerance": 1e-3,
+                         "note": "the reference sums 5.5 M float products per entry in float, the engine in double"}
+        out["cpu_baseline"] = {"value": W * H * n / t / 1e6, "unit": "MPix*iter/s", "cores": 1, "kind": "reference",
+                               "sample": "the same gradient(5), %.1f s" % t}
     return out
 
 
