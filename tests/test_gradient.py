@@ -117,6 +117,9 @@ def test_engine_gradient_matches_reference_golden(dcrf, oracle_built, case):
     gc.build(m, c, logistic=lambda Lm, f: m.setUnary(dcrf.LogisticUnary(Lm, f)))
     kind, robust, cw = objective_args(None, c, g)
     obj = engine_objective(dcrf, c, cw)
+    if c["objective"][0] == "hamming":  # Hamming(gt, class_weight_pow) builds the reference's class weights (objective.cpp:51-63)
+        own = dcrf.Hamming(c["gt"], c["objective"][1]).class_weights
+        assert np.allclose(own, cw[:own.size], rtol=1e-6, atol=0) and own.size == cw.size
     getters = (m.unaryParameters, m.labelCompatibilityParameters, m.kernelParameters)
     setters = (m.setUnaryParameters, m.setLabelCompatibilityParameters, m.setKernelParameters)
     for grp in range(3):
@@ -172,3 +175,36 @@ def test_engine_gradient_selected_outputs_and_2d_builders(dcrf, oracle_built):
         a.setKernelParameters(np.ones(3, np.float32))
     with pytest.raises(ValueError):
         a.gradient(1, dcrf.LogLikelihood(gt[:-1]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["potts_sym_ll", "two_terms_hamming", "matrix_full_iou", "logistic_before", "after_matrix"])
+def test_engine_gradient_is_the_derivative_of_the_objective(dcrf, name):
+    """Size-independent property (what the reference's gradCheck, optimization.cpp:96-118, tests): the unary and the
+    label-compatibility gradients are the exact derivatives of the objective after n mean-field iterations, so a central
+    difference of gradient()[0] over the parameter with the largest gradient reproduces that entry (2 %; the reference
+    itself shows the same agreement).  The kernel gradient is an approximation by construction (the lattice is piecewise
+    constant in the features) and is not part of this check."""
+    case = [c for c in gc.CASES if c[0] == name][0]
+    c = gc.make(case)
+    m = dcrf.DenseCRF(c["N"], c["L"])
+    gc.build(m, c, logistic=lambda Lm, f: m.setUnary(dcrf.LogisticUnary(Lm, f)))
+    cw = dcrf.Hamming(c["gt"], c["objective"][1]).class_weights if c["objective"][0] == "hamming" else ()
+    obj = engine_objective(dcrf, c, cw)
+    r = m.gradient(c["n_iter"], obj)
+    for getter, setter, g in ((m.unaryParameters, m.setUnaryParameters, r[1]),
+                              (m.labelCompatibilityParameters, m.setLabelCompatibilityParameters, r[2])):
+        if not g.size:
+            continue
+        p0 = getter()
+        j = int(np.argmax(np.abs(g)))
+        eps = 1e-2 * max(abs(float(p0[j])), 0.1)
+        vals = []
+        for sgn in (1, -1):
+            p = p0.copy()
+            p[j] += sgn * eps
+            setter(p)
+            vals.append(m.gradient(c["n_iter"], obj, unary=False, label_compatibility=False, kernel=False)[0])
+        setter(p0)
+        fd = (vals[0] - vals[1]) / (2 * eps)
+        assert abs(fd - g[j]) <= 0.02 * abs(g[j]), (name, j, float(g[j]), fd)
