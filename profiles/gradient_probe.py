@@ -32,6 +32,8 @@ m._profile_enable(False)
 print("per kernel class (name, launches, ms):", ", ".join("%s %d %.3f" % e for e in prof), flush=True)
 print("engine: gradient(%d) %.2f ms at %dx%dx%d" % (IT, t_gpu * 1e3, W, H, L), flush=True)
 
+if os.environ.get("PROBE_NO_REF"):
+    sys.exit(0)
 r = po.CRF((W, H), L, "ref")
 r.setUnaryEnergy(U)
 r.addPairwiseGaussian(3, 3)

@@ -2569,6 +2569,7 @@ dcrf_status dcrf_gradient(dcrf_t* m, int n_iterations, const dcrf_objective* obj
       if (lbl_cmp_grad) fQ = rows();
       if (kernel_grad) {
         lblQ = rows();
+        DCRF_CUDA(cudaMemsetAsync(lblQ, 0, n * sizeof(float), s));  // MatrixCompatibility leaves the pad columns alone
         w.an = rows(), w.bn = rows(), w.fa = rows(), w.fb = rows(), w.rin = rows(), w.ones = rows();
         launch_fill(cx, w.ones, n, 1.0f);
         int dmax = 1;
