@@ -203,7 +203,7 @@ void launch_splat(Ctx cx, const Lattice& lt, RowLayout rl, const float* in, cons
 // seq_math: seqCompute's arithmetic (0.5 as a double literal, permutohedral.cpp:505 / :657) whatever the channel count
 void launch_blur(Ctx cx, const Lattice& lt, RowLayout rl, int axis, const float* src, float* dst, bool seq_math = false);
 // axis `axis` then axis `axis2` in one launch (bit-identical to two launch_blur calls)
-void launch_blur2(Ctx cx, const Lattice& lt, RowLayout rl, int axis, int axis2, const float* src, float* dst);
+void launch_blur2(Ctx cx, const Lattice& lt, RowLayout rl, int axis, int axis2, const float* src, float* dst, bool seq_math = false);
 
 enum SliceMode { SLICE_WRITE = 0, SLICE_ACC_FIRST = 1, SLICE_ACC_NEXT = 2 };
 struct CompatDev {

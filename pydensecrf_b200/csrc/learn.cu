@@ -96,6 +96,96 @@ __global__ void __launch_bounds__(kThreads)
   for (int j = 0; j < d; j++) df[(size_t)i * d + j] = __fadd_rn(df[(size_t)i * d + j], g[j]);  // df[i*d_+j-1] += grad
 }
 
+// The same per-variable computation with the C = Lp/4 label chunks of a variable on C neighbouring lanes (32/C variables
+// per warp): a row read is one contiguous piece per variable instead of one scattered float4 per thread (the thread-per-
+// variable form above kept the L1 pipe 75 % busy).  Every lane forms the products of its four labels; the sum over the
+// labels stays in ascending label order by handing the running sums from lane to lane.  D = d (<= 8: the products of all
+// axes stay in registers).
+template <int D>
+__global__ void __launch_bounds__(kThreads)
+    k_lattice_grad_rows(GradParams p, int C, const PixEntry* __restrict__ pix, const uint8_t* __restrict__ rank,
+                        const float* __restrict__ val, const float* __restrict__ other, float* __restrict__ df) {
+  constexpr int dp1 = D + 1;
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31, P = 32 / C;
+  const int grp = lane / C, h = lane - grp * C, base = grp * C;
+  const long long warp_g = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long gi = warp_g * P + grp;
+  const bool act = grp < P && gi < p.N;
+  const int i = act ? (int)gi : 0;
+  int o0[dp1], o1[dp1];
+  {
+    int last = D * dp1 / 2;
+#pragma unroll
+    for (int j = 0; j <= D; j++) {
+      int rk;
+      if (j < D) {
+        rk = rank[(size_t)i * D + j];
+        last -= rk;
+      } else {
+        rk = last;
+      }
+      const int r0 = D - rk, r1 = r0 + 1 > D ? 0 : r0 + 1;
+      o0[j] = pix[(size_t)i * dp1 + r0].row;
+      o1[j] = pix[(size_t)i * dp1 + r1].row;
+    }
+  }
+  const int k4 = 4 * h;
+  float term[D][4];
+  {
+    const float4 ok4 = *reinterpret_cast<const float4*>(other + (size_t)i * p.Lp + k4);
+    const float okc[4] = {ok4.x, ok4.y, ok4.z, ok4.w};
+    float sm[4];
+    {
+      const float4 a = *reinterpret_cast<const float4*>(val + (size_t)o0[0] * p.Lp + k4);
+      const float4 b = *reinterpret_cast<const float4*>(val + (size_t)o1[0] * p.Lp + k4);
+      const float ac[4] = {a.x, a.y, a.z, a.w}, bc[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int c = 0; c < 4; c++) sm[c] = __fsub_rn(__fadd_rn(0.f, __fmul_rn(p.alpha, ac[c])), __fmul_rn(p.alpha, bc[c]));
+    }
+#pragma unroll
+    for (int j = 1; j <= D; j++) {
+      const float4 a = *reinterpret_cast<const float4*>(val + (size_t)o0[j] * p.Lp + k4);
+      const float4 b = *reinterpret_cast<const float4*>(val + (size_t)o1[j] * p.Lp + k4);
+      const float ac[4] = {a.x, a.y, a.z, a.w}, bc[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        const float ra = __fsub_rn(__fadd_rn(0.f, __fmul_rn(p.alpha, ac[c])), __fmul_rn(p.alpha, bc[c]));
+        const float v = __fmul_rn(p.scale[j - 1], __fsub_rn(sm[c], __fmul_rn((float)j, ra)));
+        term[j - 1][c] = __fmul_rn(okc[c], v);
+        sm[c] = __fadd_rn(sm[c], ra);
+      }
+    }
+  }
+  float g[D];
+#pragma unroll
+  for (int j = 0; j < D; j++) g[j] = 0.f;
+  for (int st = 0; st < C; st++) {  // lane st of every variable adds its labels, then hands the sums on
+    if (h == st) {
+#pragma unroll
+      for (int c = 0; c < 4; c++)
+        if (k4 + c < p.L) {
+#pragma unroll
+          for (int j = 0; j < D; j++) g[j] = __fadd_rn(g[j], term[j][c]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < D; j++) g[j] = __shfl_sync(full, g[j], base + st);
+  }
+  if (act && h == 0) {
+#pragma unroll
+    for (int j = 0; j < D; j++) df[(size_t)i * D + j] = __fadd_rn(df[(size_t)i * D + j], g[j]);
+  }
+}
+
+template <int D>
+void launch_grad_rows(cudaStream_t s, const GradParams& p, int C, const Lattice& lt, const float* val, const float* other, float* df) {
+  const int P = 32 / C;
+  const long long warps = ((long long)lt.N + P - 1) / P;
+  const unsigned blocks = (unsigned)((warps * 32 + kThreads - 1) / kThreads);
+  k_lattice_grad_rows<D><<<blocks, kThreads, 0, s>>>(p, C, lt.pix, lt.rank, val, other, df);
+}
+
 }  // namespace
 
 void lattice_gradient(Ctx cx, const Lattice& lt, RowLayout rl, const float* a, const float* b, float* A, float* B, float* df) {
@@ -116,11 +206,30 @@ void lattice_gradient(Ctx cx, const Lattice& lt, RowLayout rl, const float* a, c
     launch_splat(cx, lt, rl, dir ? b : a, nullptr, A);
     float *src = A, *dst = B;
     for (int t = 0; t <= d; t++) {
-      launch_blur(cx, lt, rl, dir ? d - t : t, src, dst, /*seq_math=*/true);
+      const int j = dir ? d - t : t;
+      if (t + 1 <= d) {  // two axes per launch, bit-identical to two single-axis passes
+        launch_blur2(cx, lt, rl, j, dir ? j - 1 : j + 1, src, dst, /*seq_math=*/true);
+        t++;
+      } else {
+        launch_blur(cx, lt, rl, j, src, dst, /*seq_math=*/true);
+      }
       std::swap(src, dst);
     }
     LaunchScope ls(cx.prof, cx.stream, "lattice_grad");
-    if (rl.vec == 4)
+    const float* other = dir ? a : b;
+    const int C = rl.C;
+    if (rl.vec == 4 && C <= 32 && d <= 8) {
+      switch (d) {
+        case 1: launch_grad_rows<1>(cx.stream, p, C, lt, src, other, df); break;
+        case 2: launch_grad_rows<2>(cx.stream, p, C, lt, src, other, df); break;
+        case 3: launch_grad_rows<3>(cx.stream, p, C, lt, src, other, df); break;
+        case 4: launch_grad_rows<4>(cx.stream, p, C, lt, src, other, df); break;
+        case 5: launch_grad_rows<5>(cx.stream, p, C, lt, src, other, df); break;
+        case 6: launch_grad_rows<6>(cx.stream, p, C, lt, src, other, df); break;
+        case 7: launch_grad_rows<7>(cx.stream, p, C, lt, src, other, df); break;
+        default: launch_grad_rows<8>(cx.stream, p, C, lt, src, other, df); break;
+      }
+    } else if (rl.vec == 4)
       k_lattice_grad<true><<<(lt.N + kThreads - 1) / kThreads, kThreads, 0, cx.stream>>>(p, lt.pix, lt.rank, src, dir ? a : b, df);
     else
       k_lattice_grad<false><<<(lt.N + kThreads - 1) / kThreads, kThreads, 0, cx.stream>>>(p, lt.pix, lt.rank, src, dir ? a : b, df);
@@ -184,11 +293,13 @@ __global__ void __launch_bounds__(kRedThreads)
   }
 }
 __global__ void k_outer_final(int nchunks, int nout, const double* __restrict__ part, double* __restrict__ G) {
-  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  // a warp per output: lane l adds chunks l, l + 32, ... in ascending order, then a fixed shuffle tree (deterministic)
+  const int o = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (o >= nout) return;
   double s = 0.0;
-  for (int ch = 0; ch < nchunks; ch++) s += part[(size_t)ch * nout + o];
-  G[o] = s;
+  for (int ch = lane; ch < nchunks; ch += 32) s += part[(size_t)ch * nout + o];
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
+  if (lane == 0) G[o] = s;
 }
 
 // one thread per variable ------------------------------------------------------------------------------------------
@@ -332,7 +443,7 @@ void launch_outer_sums(Ctx cx, int N, const float* A, size_t sai, size_t sar, in
   }
   {
     LaunchScope ls(cx.prof, cx.stream, "grad_outer_final");
-    k_outer_final<<<blocks_for(nout, 128), 128, 0, cx.stream>>>(nchunks, nout, part, G);
+    k_outer_final<<<blocks_for((size_t)nout * 32, 128), 128, 0, cx.stream>>>(nchunks, nout, part, G);
   }
   dev_free(part, cx.stream);
 }
