@@ -2310,25 +2310,32 @@ void term_set_kernel_params(dcrf_model* m, Term* t, const float* v) {
   g.kind = FEAT_GENERIC;
   g.feat = f0;
   materialize_features(m->cx(), g, d, N, t->ktype, dp, tf);
-  DCRF_CUDA(cudaStreamSynchronize(s));  // nothing queued may still read the old lattice
-  for (cudaStream_t a : m->aux) DCRF_CUDA(cudaStreamSynchronize(a));
-  if (!t->shared) t->lat.release(s);
-  t->shared.reset();
-  t->lat = Lattice();
-  dev_free(t->norm, s);
-  dev_free(t->valA, s);
-  dev_free(t->csr_baked, s);
-  t->norm = nullptr, t->valA = t->valB = nullptr, t->val_bytes = 0, t->csr_baked = nullptr;
+  // build the new lattice first, swap it in only when that succeeded (an allocation failure leaves the term as it was)
+  Term fresh;
+  fresh.ntype = t->ntype;
   g.feat = tf;
   try {
-    term_init_lattice(m, t, g, d);
+    term_init_lattice(m, &fresh, g, d);
   } catch (...) {
+    if (!fresh.shared) fresh.lat.release(s);
+    dev_free(fresh.norm, s);
     dev_free(dp, s);
     dev_free(tf, s);
     throw;
   }
   dev_free(dp, s);
   dev_free(tf, s);
+  DCRF_CUDA(cudaStreamSynchronize(s));  // nothing queued may still read the old lattice
+  for (cudaStream_t a : m->aux) DCRF_CUDA(cudaStreamSynchronize(a));
+  if (!t->shared) t->lat.release(s);
+  dev_free(t->norm, s);
+  dev_free(t->valA, s);
+  dev_free(t->csr_baked, s);
+  t->shared = fresh.shared;
+  t->lat = fresh.lat;
+  t->norm = fresh.norm;
+  t->valA = t->valB = nullptr, t->val_bytes = 0, t->csr_baked = nullptr;
+  fresh.norm = nullptr;  // ownership moved
   t->kparams.assign(v, v + np);
   m->drop_graphs();
 }
