@@ -33,6 +33,7 @@ cdef extern from "dcrf_b200.h" nogil:
     int dcrf_set_unary_const(dcrf_t* m, const float* u)
     int dcrf_set_unary_logistic(dcrf_t* m, const float* Lmat, int F, const float* f)
     int dcrf_set_unary_from_softmax(dcrf_t* m, const float* sm, double scale, double clip)
+    int dcrf_set_unary_from_labels(dcrf_t* m, const int32_t* labels, double gt_prob, int zero_unsure)
     int dcrf_set_unary_device(dcrf_t* m, const float* dev_u)
     int dcrf_mat_device_ptr(dcrf_mat_t* a, float** ptr, int* pitch, int* device)
     int dcrf_add_pairwise_nd(dcrf_t* m, int nsp, const int* dims, const float* sdims, int nch, const float* schan,
@@ -601,6 +602,23 @@ cdef class DenseCRF:
                 raise ValueError("Bad shape for logistic feature (Need {}, got {})".format((u.shape[1], self._nvar), (f.shape[0], f.shape[1])))
             with nogil:
                 st = dcrf_set_unary_logistic(self._h, &u[0, 0], <int>u.shape[1], &f[0, 0])
+        _check(st)
+
+    def setUnaryFromLabels(self, labels, double gt_prob, bint zero_unsure=True):
+        """setUnaryEnergy(utils.unary_from_labels(labels, nlabels, gt_prob, zero_unsure)) (utils.py:6-46) with the energies
+        formed on the device: the label map is what crosses the bus.  Same unary bit for bit."""
+        import numpy as np
+        if not (0 < gt_prob < 1):
+            raise AssertionError("`gt_prob must be in (0,1).")
+        arr = np.ascontiguousarray(np.asarray(labels).flatten(), dtype=np.int32)
+        if arr.shape[0] != self._nvar:
+            raise ValueError("Bad shape for labels (Need {} entries, got {})".format(self._nvar, arr.shape[0]))
+        cdef int32_t[::1] v = arr
+        cdef int st
+        with nogil:
+            st = dcrf_set_unary_from_labels(self._h, &v[0], gt_prob, 1 if zero_unsure else 0)
+        if st == 1 and b"out of bounds" in dcrf_last_error():
+            raise IndexError(dcrf_last_error().decode())
         _check(st)
 
     def inference(self, int niter):

@@ -1335,6 +1335,54 @@ dcrf_status dcrf_set_unary_from_softmax(dcrf_t* m, const float* sm_LxN, double s
     DCRF_CUDA(cudaStreamSynchronize(m->stream));
   });
 }
+// utils.unary_from_labels (pydensecrf/utils.py:6-46) evaluated on the device: one int32 label per variable crosses the bus
+// instead of nlabels floats.  row / unsure follow numpy's indexing of `U[labels - 1 if zero_unsure else labels, arange]`
+// (negative indices wrap once) and `labels == 0`.
+namespace {
+__global__ void k_unary_from_labels(int N, int L, int Lp, const int32_t* __restrict__ labels, int zero_unsure, float e_label,
+                                    float e_other, float e_unsure, float* __restrict__ U) {
+  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= (size_t)N * Lp) return;
+  const size_t i = q / Lp;
+  const int l = (int)(q - i * Lp);
+  const int lab = labels[i];
+  int row = zero_unsure ? lab - 1 : lab;
+  if (row < 0) row += L;
+  float v = 0.f;
+  if (l < L) v = (zero_unsure && lab == 0) ? e_unsure : (l == row ? e_label : e_other);
+  U[q] = v;
+}
+}  // namespace
+dcrf_status dcrf_set_unary_from_labels(dcrf_t* m, const int32_t* labels_N, double gt_prob, int zero_unsure) {
+  return guarded([&] {
+    DCRF_REQUIRE(m && labels_N, "null argument");
+    DCRF_REQUIRE(gt_prob > 0.0 && gt_prob < 1.0, "`gt_prob must be in (0,1).");
+    const int N = m->N, L = m->L;
+    for (int i = 0; i < N; i++) {  // numpy raises IndexError for a row outside [-L, L)
+      const long long row = (long long)labels_N[i] - (zero_unsure ? 1 : 0);
+      DCRF_REQUIRE(row >= -(long long)L && row < (long long)L, "label " + std::to_string(labels_N[i]) + " of variable " +
+                                                                   std::to_string(i) + " is out of bounds for " + std::to_string(L) + " labels");
+    }
+    DeviceGuard g(m->device);
+    forget_logistic(m);
+    int32_t* dl = (int32_t*)upload_tmp(m, labels_N, (size_t)N * sizeof(int32_t));
+    if (!m->U) {
+      m->U = dev_alloc<float>((size_t)N * m->rl.Lp, m->stream);
+      m->drop_graphs();
+    }
+    const float e_other = (float)-std::log((1.0 - gt_prob) / (L - 1)), e_label = (float)-std::log(gt_prob),
+                e_unsure = (float)-std::log(1.0 / L);
+    {
+      LaunchScope ls(&m->prof, m->stream, "unary_from_labels");
+      const size_t n = (size_t)N * m->rl.Lp;
+      k_unary_from_labels<<<(unsigned)((n + 255) / 256), 256, 0, m->stream>>>(N, L, m->rl.Lp, dl, zero_unsure ? 1 : 0, e_label, e_other,
+                                                                              e_unsure, m->U);
+    }
+    dev_free(dl, m->stream);
+    DCRF_CUDA(cudaGetLastError());
+    DCRF_CUDA(cudaStreamSynchronize(m->stream));
+  });
+}
 dcrf_status dcrf_set_unary_logistic(dcrf_t* m, const float* Lmat_LxF, int F, const float* f_FxN) {
   return guarded([&] {
     DCRF_REQUIRE(m && Lmat_LxF && f_FxN && F >= 1, "bad argument");

@@ -290,3 +290,34 @@ def test_results_kept_alive_fall_back_to_ordinary_memory(dcrf):
         assert m16.dtype == np.int16 and np.array_equal(m16, maps16[0])
         assert np.array_equal(q, qs[0])
     assert np.array_equal(maps[0], np.argmax(qs[0], axis=0))
+
+
+@pytest.mark.parametrize("zero_unsure", [True, False])
+def test_unary_from_labels_on_device(dcrf, zero_unsure):
+    """setUnaryFromLabels forms utils.unary_from_labels' energies (reference utils.py:6-46) on the device from the int32
+    label map: the same unary bit for bit (Q0 = softmax(-U) and the iterations agree exactly), numpy's index errors kept."""
+    from pydensecrf_b200 import utils
+    from tests import workloads as wl
+
+    W, H, L = 57, 41, 5
+    rng = np.random.default_rng(5)
+    img = wl.smooth_image(H, W, seed=2, grid=8)
+    labels = rng.integers(0, L + 1 if zero_unsure else L, (H, W))
+    for gt_prob in (0.5, 0.7, 0.93):
+        a = dcrf.DenseCRF2D(W, H, L)
+        a.setUnaryEnergy(utils.unary_from_labels(labels, L, gt_prob, zero_unsure))
+        b = dcrf.DenseCRF2D(W, H, L)
+        b.setUnaryFromLabels(labels, gt_prob, zero_unsure)
+        for m in (a, b):
+            m.addPairwiseGaussian(3, 3)
+            m.addPairwiseBilateral(40, 13, img, 10)
+        for n in (0, 3):
+            assert np.array_equal(np.array(a.inference(n)), np.array(b.inference(n))), (gt_prob, n)
+    bad = labels.copy()
+    bad[3, 4] = L + 2
+    with pytest.raises(IndexError):
+        b.setUnaryFromLabels(bad, 0.5, zero_unsure)
+    with pytest.raises(ValueError):
+        b.setUnaryFromLabels(labels[:-1], 0.5, zero_unsure)
+    with pytest.raises(AssertionError):
+        b.setUnaryFromLabels(labels, 1.0, zero_unsure)
