@@ -432,6 +432,7 @@ void launch_outer_sums(Ctx cx, int N, const float* A, size_t sai, size_t sar, in
   const int nout = diag ? ra : ra * rb;
   const int TP = std::max(1, std::min(64, (int)(kTileBytes / ((size_t)(ra + rb) * sizeof(float)))));
   int nchunks = std::max(1, std::min(592, (N + 4 * TP - 1) / (4 * TP)));
+  nchunks = (int)std::max<size_t>(1, std::min<size_t>((size_t)nchunks, ((size_t)256 << 20) / ((size_t)nout * sizeof(double))));  // partials <= 256 MB
   const int per_chunk = (N + nchunks - 1) / nchunks;
   nchunks = (N + per_chunk - 1) / per_chunk;
   double* part = dev_alloc<double>((size_t)nchunks * nout, cx.stream);

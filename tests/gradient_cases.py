@@ -14,6 +14,7 @@ CASES = [
     ("nonorm_const_kernel", 280, 4, "logistic", [(3, POTTS, 0, 0), (2, POTTS, 1, 0)], ("iou",), 2),
     ("labels21", 500, 21, "const", [(2, POTTS, 1, 3), (5, POTTS, 2, 3)], ("ll", 0.0), 2),
     ("two_labels", 200, 2, "const", [(2, DIAG, 1, 3)], ("ll", 0.0), 4),
+    ("labels70_matrix", 320, 70, "const", [(3, MATRIX, 1, 3)], ("ll", 0.0), 2),   # tensor-core MatrixCompatibility (>= 64 labels), 4 900 sums
     ("no_terms", 128, 3, "logistic", [], ("hamming", 1.0), 2),
     ("zero_iterations", 150, 4, "logistic", [(2, POTTS, 1, 3)], ("iou",), 0),
 ]
