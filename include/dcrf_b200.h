@@ -242,6 +242,11 @@ dcrf_status dcrf_pairwise_apply_transpose(dcrf_t* m, int k, dcrf_mat_t* Q, dcrf_
  * variable i, for pixel-major a, b (N rows of L floats, the layout of MatrixXf::data()); df: N rows of d floats.
  * DenseKernel::kernelGradient (pairwise.cpp:82-86) is exactly this call. */
 dcrf_status dcrf_lattice_gradient(dcrf_t* m, int k, const float* a_NxL, const float* b_NxL, int L, float* df_Nxd);
+/* DenseCRF::unaryEnergy / pairwiseEnergy (densecrf.cpp:141-177, densecrf.h:88-91; not wrapped by densecrf.pyx): the energy
+ * every variable contributes under a labelling -- unary(l_i, i), and -0.5 * (apply of the one-hot belief)(l_i, i) for
+ * pairwise term `term` (-1: summed over all terms in order).  Labels outside [0, nlabels) give 0.  out_N: N floats. */
+dcrf_status dcrf_unary_energy(dcrf_t* m, const int16_t* labels_N, float* out_N);
+dcrf_status dcrf_pairwise_energy(dcrf_t* m, const int16_t* labels_N, int term, float* out_N);
 /* DenseCRF::gradient (densecrf.cpp:237-297, declared densecrf.h:106): runs n_iterations of mean field keeping every Q,
  * evaluates the objective on the last one and back-propagates through the iterations.  Any gradient pointer may be NULL
  * (that gradient is not computed); each receives as many floats as dcrf_num_parameters reports for its group, in the

@@ -109,6 +109,8 @@ class _Lib:
             self.crf_set_params = fn("crf_set_params", None, vp, C.c_int, _fp, C.c_int)
             self.crf_gradient = fn("crf_gradient", C.c_double, vp, C.c_int, C.c_int, sp, C.c_float, _fp, C.c_int, _fp, _fp, _fp)
             self.hamming_weights = fn("hamming_weights", None, sp, C.c_int, C.c_float, C.c_int, _fp)
+            self.crf_unary_energy = fn("crf_unary_energy", None, vp, sp, _fp)
+            self.crf_pairwise_energy = fn("crf_pairwise_energy", None, vp, sp, C.c_int, _fp)
 
 
 _libs = {}
@@ -308,6 +310,24 @@ def _ref_gradient(self, n_iter, kind, gt, robust=0.0, class_weight=(), unary=Tru
     return (float(r),) + tuple(outs)
 
 
+def _ref_unary_energy(self, labels):
+    """DenseCRF::unaryEnergy of the UNMODIFIED reference (which="ref" only)."""
+    lab = np.ascontiguousarray(labels, dtype=np.int16).ravel()
+    out = np.zeros(self.N, np.float32)
+    self.lib.crf_unary_energy(self.h, _ptr(lab, C.POINTER(C.c_short)), _ptr(out))
+    return out
+
+
+def _ref_pairwise_energy(self, labels, term=-1):
+    """DenseCRF::pairwiseEnergy of the UNMODIFIED reference (which="ref" only)."""
+    lab = np.ascontiguousarray(labels, dtype=np.int16).ravel()
+    out = np.zeros(self.N, np.float32)
+    self.lib.crf_pairwise_energy(self.h, _ptr(lab, C.POINTER(C.c_short)), int(term), _ptr(out))
+    return out
+
+
+CRF.unaryEnergy = _ref_unary_energy
+CRF.pairwiseEnergy = _ref_pairwise_energy
 CRF.parameters = _ref_params
 CRF.setParameters = _ref_set_params
 CRF.gradient = _ref_gradient

@@ -199,6 +199,17 @@ void ref_pairwise_apply(const float* feat_dxN, int d, int N, int L, int compat_k
   pp.apply(out, Q);
   std::memcpy(out_NxL, out.data(), sizeof(float) * (size_t)L * N);
 }
+// DenseCRF::unaryEnergy / pairwiseEnergy (densecrf.cpp:141-177)
+void ref_crf_unary_energy(void* h, const short* labels, float* out_N) {
+  Model* m = static_cast<Model*>(h);
+  VectorXf r = m->crf->unaryEnergy(VectorXs(Eigen::Map<const VectorXs>(labels, m->N)));
+  std::memcpy(out_N, r.data(), sizeof(float) * m->N);
+}
+void ref_crf_pairwise_energy(void* h, const short* labels, int term, float* out_N) {
+  Model* m = static_cast<Model*>(h);
+  VectorXf r = m->crf->pairwiseEnergy(VectorXs(Eigen::Map<const VectorXs>(labels, m->N)), term);
+  std::memcpy(out_N, r.data(), sizeof(float) * m->N);
+}
 // ---- learning path: the reference's own DenseCRF::gradient and parameter vectors (densecrf.h:106-124) ----------------
 // group: 0 unary, 1 label compatibility, 2 kernel
 static VectorXf ref_params(Model* m, int group) {

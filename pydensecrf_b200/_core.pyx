@@ -86,6 +86,8 @@ cdef extern from "dcrf_b200.h" nogil:
         int n_class_weight
     int dcrf_gradient(dcrf_t* m, int n_iterations, const dcrf_objective* objective, double* value, float* unary_grad,
                       float* lbl_cmp_grad, float* kernel_grad)
+    int dcrf_unary_energy(dcrf_t* m, const int16_t* labels, float* out)
+    int dcrf_pairwise_energy(dcrf_t* m, const int16_t* labels, int term, float* out)
     int dcrf_num_parameters(dcrf_t* m, int group, int* n)
     int dcrf_get_parameters(dcrf_t* m, int group, float* out)
     int dcrf_set_parameters(dcrf_t* m, int group, const float* v, int n)
@@ -922,6 +924,40 @@ cdef class DenseCRF:
         _check(st)
         return out
 
+
+    def _labels_arg(self, labels):
+        import numpy as np
+        arr = np.ascontiguousarray(np.asarray(labels).flatten(), dtype=np.int16)
+        if arr.shape[0] != self._nvar:
+            raise ValueError("Bad shape for labels (Need {} entries, got {})".format(self._nvar, arr.shape[0]))
+        return arr
+
+    def unaryEnergy(self, labels):
+        """DenseCRF::unaryEnergy (densecrf.cpp:141-153): float32 (nvar,), unary(l_i, i) of every variable."""
+        import numpy as np
+        arr = self._labels_arg(labels)
+        out = np.empty(self._nvar, np.float32)
+        cdef int16_t[::1] v = arr
+        cdef float[::1] o = out
+        cdef int st
+        with nogil:
+            st = dcrf_unary_energy(self._h, &v[0], &o[0])
+        _check(st)
+        return out
+
+    def pairwiseEnergy(self, labels, int term=-1):
+        """DenseCRF::pairwiseEnergy (densecrf.cpp:154-177): float32 (nvar,), -0.5 * apply(one-hot belief)(l_i, i) of pairwise
+        term `term`, or of all terms summed (term = -1)."""
+        import numpy as np
+        arr = self._labels_arg(labels)
+        out = np.empty(self._nvar, np.float32)
+        cdef int16_t[::1] v = arr
+        cdef float[::1] o = out
+        cdef int st
+        with nogil:
+            st = dcrf_pairwise_energy(self._h, &v[0], term, &o[0])
+        _check(st)
+        return out
 
     # ---- learning path (densecrf.h:106-124; not wrapped by the reference's densecrf.pyx) ------------------------------
     def _get_params(self, int group):

@@ -2323,6 +2323,69 @@ dcrf_status dcrf_lattice_gradient(dcrf_t* m, int k, const float* a_NxL, const fl
     DCRF_CUDA(cudaStreamSynchronize(s));
   });
 }
+// ---- energies of a labelling: DenseCRF::unaryEnergy / pairwiseEnergy (densecrf.cpp:141-177, the "Debug" block) -------------
+namespace {
+__global__ void k_one_hot(int N, int L, int Lp, const int16_t* __restrict__ lab, float* __restrict__ Q) {
+  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= (size_t)N * Lp) return;
+  const size_t i = q / Lp;
+  const int l = (int)(q - i * Lp);
+  Q[q] = (l < L && lab[i] == l) ? 1.f : 0.f;  // Q(j, i) = (l[i] == j)  (:169)
+}
+// out[i] (+)= scale * src(l[i], i) for labels inside [0, L), else 0  (:149-150, :172-175)
+__global__ void k_pick_label(int N, int L, int Lp, const int16_t* __restrict__ lab, const float* __restrict__ src, float scale,
+                             int accumulate, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const int l = lab[i];
+  const float v = (l >= 0 && l < L) ? __fmul_rn(scale, src[(size_t)i * Lp + l]) : 0.f;
+  out[i] = accumulate ? __fadd_rn(out[i], v) : v;
+}
+dcrf_status labelling_energy(dcrf_t* m, const int16_t* labels_N, bool pairwise, int term, float* out_N) {
+  return guarded([&] {
+    DCRF_REQUIRE(m && labels_N && out_N, "null argument");
+    const int nt = (int)m->terms.size();
+    DCRF_REQUIRE(!pairwise || (term >= -1 && term < nt), "no such pairwise term");
+    DeviceGuard g(m->device);
+    Ctx cx = m->cx();
+    cudaStream_t s = m->stream;
+    const int N = m->N, L = m->L, Lp = m->rl.Lp;
+    const size_t n = (size_t)N * Lp;
+    int16_t* lab = (int16_t*)upload_tmp(m, labels_N, (size_t)N * sizeof(int16_t));
+    float* r = dev_alloc<float>(N, s);
+    DCRF_CUDA(cudaMemsetAsync(r, 0, (size_t)N * sizeof(float), s));
+    float *Q = nullptr, *msg = nullptr;
+    const unsigned nb = (unsigned)((N + 255) / 256);
+    if (!pairwise) {
+      if (m->U) {
+        LaunchScope ls(cx.prof, s, "labelling_energy");
+        k_pick_label<<<nb, 256, 0, s>>>(N, L, Lp, lab, m->U, 1.f, 0, r);
+      }
+    } else if (nt > 0) {
+      Q = dev_alloc<float>(n, s);
+      msg = dev_alloc<float>(n, s);
+      {
+        LaunchScope ls(cx.prof, s, "labelling_energy");
+        k_one_hot<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(N, L, Lp, lab, Q);
+      }
+      for (int k = (term < 0 ? 0 : term); k < (term < 0 ? nt : term + 1); k++) {
+        term_apply(m, m->terms[k], Q, SLICE_WRITE, false, msg);  // pairwise_[term]->apply(Q, Q)  (:170)
+        LaunchScope ls(cx.prof, s, "labelling_energy");
+        k_pick_label<<<nb, 256, 0, s>>>(N, L, Lp, lab, msg, -0.5f, term < 0 ? 1 : 0, r);  // r += ... over the terms (:160-161)
+      }
+    }
+    DCRF_CUDA(cudaMemcpyAsync(out_N, r, (size_t)N * sizeof(float), cudaMemcpyDeviceToHost, s));
+    for (void* p : {(void*)lab, (void*)r, (void*)Q, (void*)msg}) dev_free(p, s);
+    DCRF_CUDA(cudaGetLastError());
+    DCRF_CUDA(cudaStreamSynchronize(s));
+  });
+}
+}  // namespace
+dcrf_status dcrf_unary_energy(dcrf_t* m, const int16_t* labels_N, float* out_N) { return labelling_energy(m, labels_N, false, 0, out_N); }
+dcrf_status dcrf_pairwise_energy(dcrf_t* m, const int16_t* labels_N, int term, float* out_N) {
+  return labelling_energy(m, labels_N, true, term, out_N);
+}
+
 // ---- learning path: parameter vectors and DenseCRF::gradient ------------------------------------------------------
 namespace {
 int n_compat_params(const dcrf_model* m, const Term* t) {

@@ -321,3 +321,35 @@ def test_unary_from_labels_on_device(dcrf, zero_unsure):
         b.setUnaryFromLabels(labels[:-1], 0.5, zero_unsure)
     with pytest.raises(AssertionError):
         b.setUnaryFromLabels(labels, 1.0, zero_unsure)
+
+
+def test_labelling_energies_match_the_reference(dcrf, oracle_built):
+    """DenseCRF::unaryEnergy / pairwiseEnergy (densecrf.cpp:141-177) against the unmodified reference: per-variable
+    energies of a labelling, single terms and their sum, labels outside [0, L) giving 0.  The filter is bit-faithful, so
+    the Potts / Diagonal energies are equal bit for bit."""
+    if not oracle_built.available("ref"):
+        pytest.skip("oracle/_ref/libref.so not present")
+    from tests import workloads as wl
+
+    W, H, L = 40, 30, 5
+    img = wl.smooth_image(H, W, seed=1, grid=8)
+    U = wl.softmax_unary(H, W, L, seed=1, grid=8)
+    lab = np.random.default_rng(0).integers(-1, L + 1, W * H).astype(np.int16)
+    diag = np.linspace(0.5, 2.0, L).astype(np.float32)
+    for nt in (0, 3):
+        d = dcrf.DenseCRF2D(W, H, L)
+        c = oracle_built.CRF((W, H), L, "ref")
+        assert np.array_equal(d.unaryEnergy(lab), np.zeros(W * H, np.float32))      # no unary set
+        for m in (d, c):
+            m.setUnaryEnergy(U)
+        d.addPairwiseGaussian(3, 3.0, normalization=dcrf.NormalizationType(nt))
+        d.addPairwiseBilateral(40, 13, img, diag, normalization=dcrf.NormalizationType(nt))
+        c.addPairwiseGaussian(3, 3.0, normalization=nt)
+        c.addPairwiseBilateral(40, 13, img, diag, normalization=nt)
+        assert np.array_equal(d.unaryEnergy(lab), c.unaryEnergy(lab))
+        for term in (0, 1, -1):
+            assert np.array_equal(d.pairwiseEnergy(lab, term), c.pairwiseEnergy(lab, term)), (nt, term)
+    with pytest.raises(ValueError):
+        d.pairwiseEnergy(lab, 2)
+    with pytest.raises(ValueError):
+        d.unaryEnergy(lab[:-1])
