@@ -2739,7 +2739,7 @@ dcrf_status dcrf_gradient(dcrf_t* m, int n_iterations, const dcrf_objective* obj
     }
     std::vector<double> h(std::max<size_t>(total, 1));
     DCRF_CUDA(cudaGetLastError());
-    DCRF_CUDA(cudaMemcpyAsync(h.data(), res, h.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (total > 0) DCRF_CUDA(cudaMemcpyAsync(h.data(), res, total * sizeof(double), cudaMemcpyDeviceToHost, s));
     DCRF_CUDA(cudaStreamSynchronize(s));
 
     // the reference's float accumulation over iterations and terms, in its order
