@@ -2325,6 +2325,14 @@ dcrf_status dcrf_lattice_gradient(dcrf_t* m, int k, const float* a_NxL, const fl
 }
 // ---- energies of a labelling: DenseCRF::unaryEnergy / pairwiseEnergy (densecrf.cpp:141-177, the "Debug" block) -------------
 namespace {
+struct DevScratch {  // device buffers of one call, released in stream order however the call ends
+  cudaStream_t s;
+  std::vector<void*> v;
+  void add(void* p) { v.push_back(p); }
+  ~DevScratch() {
+    for (void* p : v) dev_free(p, s);
+  }
+};
 __global__ void k_one_hot(int N, int L, int Lp, const int16_t* __restrict__ lab, float* __restrict__ Q) {
   const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= (size_t)N * Lp) return;
@@ -2351,8 +2359,11 @@ dcrf_status labelling_energy(dcrf_t* m, const int16_t* labels_N, bool pairwise, 
     cudaStream_t s = m->stream;
     const int N = m->N, L = m->L, Lp = m->rl.Lp;
     const size_t n = (size_t)N * Lp;
+    DevScratch tmp{s, {}};
     int16_t* lab = (int16_t*)upload_tmp(m, labels_N, (size_t)N * sizeof(int16_t));
+    tmp.add(lab);
     float* r = dev_alloc<float>(N, s);
+    tmp.add(r);
     DCRF_CUDA(cudaMemsetAsync(r, 0, (size_t)N * sizeof(float), s));
     float *Q = nullptr, *msg = nullptr;
     const unsigned nb = (unsigned)((N + 255) / 256);
@@ -2363,7 +2374,9 @@ dcrf_status labelling_energy(dcrf_t* m, const int16_t* labels_N, bool pairwise, 
       }
     } else if (nt > 0) {
       Q = dev_alloc<float>(n, s);
+      tmp.add(Q);
       msg = dev_alloc<float>(n, s);
+      tmp.add(msg);
       {
         LaunchScope ls(cx.prof, s, "labelling_energy");
         k_one_hot<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(N, L, Lp, lab, Q);
@@ -2375,7 +2388,6 @@ dcrf_status labelling_energy(dcrf_t* m, const int16_t* labels_N, bool pairwise, 
       }
     }
     DCRF_CUDA(cudaMemcpyAsync(out_N, r, (size_t)N * sizeof(float), cudaMemcpyDeviceToHost, s));
-    for (void* p : {(void*)lab, (void*)r, (void*)Q, (void*)msg}) dev_free(p, s);
     DCRF_CUDA(cudaGetLastError());
     DCRF_CUDA(cudaStreamSynchronize(s));
   });
