@@ -75,3 +75,19 @@ def kernel_param_update(c, rng):
         elif ktype == 2:
             out.append((np.eye(d) + rng.uniform(-0.15, 0.15, (d, d))).T.ravel())
     return np.concatenate(out).astype(np.float32) if out else np.zeros(0, np.float32)
+
+
+def fuzz_case(seed):
+    """A random small model for the fuzz tests: any unary kind, 0-3 terms of random feature dimension, compatibility,
+    kernel and normalisation type, any objective, 0-3 iterations."""
+    rng = np.random.default_rng(1000 + seed)
+    N = int(rng.integers(40, 500))
+    L = int(rng.choice([2, 3, 4, 5, 8, 13, 21, 24]))
+    unary = [None, "const", "logistic"][int(rng.integers(0, 3))]
+    terms = []
+    for _ in range(int(rng.integers(0, 4))):
+        terms.append((int(rng.integers(1, 7)), [POTTS, DIAG, MATRIX][int(rng.integers(0, 3))], int(rng.integers(0, 3)),
+                      int(rng.integers(0, 4))))
+    kind = ["ll", "hamming", "iou"][int(rng.integers(0, 3))]
+    objective = (kind, float(rng.choice([0.0, 0.05]))) if kind == "ll" else (kind, 0.0) if kind == "hamming" else (kind,)
+    return ("fuzz%d" % seed, N, L, unary, terms, objective, int(rng.integers(0, 4)))
