@@ -252,7 +252,7 @@ dcrf_status dcrf_pairwise_energy(dcrf_t* m, const int16_t* labels_N, int term, f
  * (that gradient is not computed); each receives as many floats as dcrf_num_parameters reports for its group, in the
  * reference's packing.  *value receives ObjectiveFunction::evaluate's return value.  Sums over the variables are taken in
  * double in a fixed order (deterministic); against the reference's float Eigen reductions the gradients agree to ~1e-4
- * relative (tests/test_gpu_gradient.py states the tolerances). */
+ * relative (tests/test_gradient.py states the tolerances). */
 typedef enum { DCRF_OBJECTIVE_LOGLIKELIHOOD = 0, DCRF_OBJECTIVE_HAMMING = 1, DCRF_OBJECTIVE_IOU = 2 } dcrf_objective_kind;
 typedef struct {
   int kind;                  /* dcrf_objective_kind: LogLikelihood / Hamming / IntersectionOverUnion (objective.h:38-74) */
