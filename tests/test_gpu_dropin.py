@@ -122,3 +122,71 @@ def test_c_abi_with_ctypes_only(oracle_built):
     Qo = o.inference(5)
     assert np.abs(q - Qo).max() <= 2e-6
     assert np.array_equal(labels, np.argmax(q, axis=0))
+
+
+def test_c_abi_learning_path_with_ctypes_only(oracle_built):
+    """dcrf_gradient, dcrf_{num,get,set}_parameters and dcrf_{unary,pairwise}_energy driven through ctypes alone (the
+    dcrf_objective struct as a C structure), against the numpy restatement of the reference's gradient."""
+    from tests import workloads as wl
+
+    lib = C.CDLL(os.path.join(ROOT, "pydensecrf_b200", "libdcrf_b200.so"))
+    vp, fp, sp = C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int16)
+
+    class Objective(C.Structure):   # include/dcrf_b200.h: dcrf_objective
+        _fields_ = [("kind", C.c_int), ("gt", sp), ("robust", C.c_float), ("class_weight", fp), ("n_class_weight", C.c_int)]
+
+    lib.dcrf_last_error.restype = C.c_char_p
+    lib.dcrf_create.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+    lib.dcrf_set_unary_const.argtypes = [vp, fp]
+    lib.dcrf_add_pairwise_energy.argtypes = [vp, fp, C.c_int, C.c_int, fp, C.c_int, C.c_int]
+    lib.dcrf_num_parameters.argtypes = [vp, C.c_int, C.POINTER(C.c_int)]
+    lib.dcrf_get_parameters.argtypes = [vp, C.c_int, fp]
+    lib.dcrf_set_parameters.argtypes = [vp, C.c_int, fp, C.c_int]
+    lib.dcrf_gradient.argtypes = [vp, C.c_int, C.POINTER(Objective), C.POINTER(C.c_double), fp, fp, fp]
+    lib.dcrf_unary_energy.argtypes = [vp, sp, fp]
+    lib.dcrf_pairwise_energy.argtypes = [vp, sp, C.c_int, fp]
+    lib.dcrf_destroy.argtypes = [vp]
+    lib.dcrf_destroy.restype = None
+
+    def ok(st):
+        assert st == 0, lib.dcrf_last_error().decode()
+
+    N, L, d = 300, 4, 3
+    rng = np.random.default_rng(9)
+    U = rng.standard_normal((L, N)).astype(np.float32)
+    f = (np.cumsum(rng.standard_normal((d, N)) * 0.3, axis=1)).astype(np.float32)
+    gt = rng.integers(0, L, N).astype(np.int16)
+    m = vp()
+    ok(lib.dcrf_create(N, L, 0, C.byref(m)))
+    ok(lib.dcrf_set_unary_const(m, U.ctypes.data_as(fp)))
+    w = (C.c_float * 1)(2.0)
+    ok(lib.dcrf_add_pairwise_energy(m, f.ctypes.data_as(fp), d, 0, w, 1, 3))     # Potts, DIAG_KERNEL, NORMALIZE_SYMMETRIC
+    n = [C.c_int() for _ in range(3)]
+    for g in range(3):
+        ok(lib.dcrf_num_parameters(m, g, C.byref(n[g])))
+    assert [x.value for x in n] == [0, 1, d]
+    kp = np.zeros(d, np.float32)
+    ok(lib.dcrf_get_parameters(m, 2, kp.ctypes.data_as(fp)))
+    assert np.array_equal(kp, np.ones(d, np.float32))
+    obj = Objective(0, gt.ctypes.data_as(sp), 0.0, None, 0)
+    val = C.c_double()
+    gl, gk = np.zeros(1, np.float32), np.zeros(d, np.float32)
+    ok(lib.dcrf_gradient(m, 3, C.byref(obj), C.byref(val), None, gl.ctypes.data_as(fp), gk.ctypes.data_as(fp)))
+    r = oracle_built.GradientRestated(N, L)
+    r.setUnaryEnergy(U)
+    r.addPairwiseEnergy(f, 2.0)
+    want = r.gradient(3, 0, gt)
+    assert abs(val.value - want[0]) <= 1e-6 * abs(want[0])
+    assert np.abs(gl - want[2]).max() <= 2e-4 * np.abs(want[2]).max() + 5e-7
+    assert np.abs(gk - want[3]).max() <= 2e-4 * np.abs(want[3]).max() + 5e-7
+    new = np.array([3.5], np.float32)
+    ok(lib.dcrf_set_parameters(m, 1, new.ctypes.data_as(fp), 1))
+    assert lib.dcrf_set_parameters(m, 1, new.ctypes.data_as(fp), 2) == 1          # DCRF_EINVAL: wrong count
+    e_u, e_p = np.zeros(N, np.float32), np.zeros(N, np.float32)
+    ok(lib.dcrf_unary_energy(m, gt.ctypes.data_as(sp), e_u.ctypes.data_as(fp)))
+    ok(lib.dcrf_pairwise_energy(m, gt.ctypes.data_as(sp), -1, e_p.ctypes.data_as(fp)))
+    assert np.array_equal(e_u, U[gt, np.arange(N)])
+    onehot = np.eye(L, dtype=np.float32)[gt]                                      # (N, L)
+    t = r.terms[0]
+    assert np.allclose(e_p, -0.5 * (-3.5 * r._kernel_apply(t, onehot))[np.arange(N), gt], rtol=1e-6, atol=1e-7)
+    lib.dcrf_destroy(m)
